@@ -1,0 +1,221 @@
+/*
+ * romab200.h — C ABI of the B200-native RoMa dense-matching kernels (libromab200.so).
+ *
+ * Drop-in boundary for ONE path: RoMa's dense match()/sample() inference.  The reference
+ * (Parskatt/RoMa) is pure Python/PyTorch; the only native operator boundary it has on this path is
+ * the optional third-party wheel `local_corr.local_corr` (romatch/utils/local_correlation.py:22-35).
+ * Every entry point below cites the reference code it replaces.  Conventions:
+ *
+ *   - plain pointers and sizes only (no torch types); every pointer is DEVICE memory owned by the
+ *     caller (PyTorch's allocator in the host package); nothing is allocated or synchronised inside;
+ *   - every call enqueues work on the given CUDA stream (a `cudaStream_t` passed as void*) and returns
+ *     immediately: 0 = ok, non-zero = error, message via romab200_last_error() (thread-local);
+ *   - activations are channels-last ("NHWC"): a [B,H,W,C] map is a row-major [B*H*W, C] matrix with an
+ *     explicit row pitch, so 1x1 convolutions and Linear layers are the same GEMM;
+ *   - dtypes: RB_F32 / RB_F16 / RB_BF16; accumulation is always fp32.
+ */
+#ifndef ROMAB200_H
+#define ROMAB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ROMAB200_ABI_VERSION 1
+
+enum rb_dtype { RB_F32 = 0, RB_F16 = 1, RB_BF16 = 2 };
+enum rb_act { RB_ACT_NONE = 0, RB_ACT_RELU = 1, RB_ACT_GELU = 2 };
+enum rb_rowmap { RB_ROWMAP_NONE = 0, RB_ROWMAP_PAD_KEEP = 1, RB_ROWMAP_PAD_TO_COMPACT = 2, RB_ROWMAP_SEGMENT = 3 };
+enum rb_epi { RB_EPI_LINEAR = 0, RB_EPI_COSKERNEL = 1 };
+enum rb_backend { RB_BACKEND_AUTO = 0, RB_BACKEND_SIMT = 1, RB_BACKEND_TCGEN05 = 2 };
+
+int romab200_abi_version(void);
+const char* romab200_last_error(void);
+/* 1 if the running device is sm_100 (B200) and the tcgen05/TMA kernels may be launched */
+int romab200_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM with fused epilogue:  C[m,n] = epi( sum_k A[m + tap(k), k] * B[n,k] )
+ *
+ * Replaces every nn.Linear / 1x1 nn.Conv2d (+ folded BatchNorm) / 3x3 nn.Conv2d on the path:
+ *   ViT + decoder Linear layers      romatch/models/transformer/layers/{attention.py:50-63,mlp.py:35-41}
+ *   proj[s] 1x1 conv + BN            romatch/models/model_zoo/roma_models.py:156-169 (matcher.py:441-450)
+ *   ConvRefiner pointwise convs      romatch/models/matcher.py:121 (create_block conv2)
+ *   VGG19-BN 3x3 conv + BN + ReLU    romatch/models/encoders.py:17-27 (as a 9-tap shifted GEMM on a
+ *                                    zero-padded NHWC map: tap t reads rows m + tap_rows[t])
+ *   CosKernel all-pairs contraction  romatch/models/matcher.py:191-200 (RB_EPI_COSKERNEL)
+ *   attention QK^T / PV, GP K_xy@alpha, Cholesky trailing updates (batched, strided)
+ *
+ * A: [M, K] row-major (pitch lda).  B: [N, K] row-major (pitch ldb), or [K, N] when trans_b != 0.
+ * K = ntaps * k_per_tap; element k belongs to tap k / k_per_tap and reads A row m + tap_rows[tap]
+ * (rows outside [0, a_rows) read as zero).  Batching: grid over batch0 x batch1 with element strides.
+ *
+ * Epilogue RB_EPI_LINEAR:    v = alpha*acc + bias[n]; v = act(v); v *= col_scale[n]; v += R[m,n]
+ * Epilogue RB_EPI_COSKERNEL: c = acc * s(m,n), s = 1/(na[m]*nb[n]+eps)            (cos_normalized == 0)
+ *                                              s = na[m]*nb[n]/(na[m]*nb[n]+eps)  (operands pre-normalised)
+ *                            v = exp((c - 1) * inv_t) + (m == n ? diag_add : 0)
+ * Row map of the store: NONE; PAD_KEEP (m indexes a zero-padded [*,pad_h,pad_w] grid, border rows are
+ * not written); PAD_TO_COMPACT (same, interior rows are written to the un-padded row index);
+ * SEGMENT (row m -> (m / seg_in) * seg_out + m % seg_in + seg_off).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    const void* A; const void* B; void* C;
+    int32_t M, N, K;
+    int64_t lda, ldb, ldc;
+    int32_t dtype_ab, dtype_c;
+    int32_t trans_b;
+    int32_t batch0, batch1;
+    int64_t sa0, sa1, sb0, sb1, sc0, sc1;
+    int32_t ntaps; int32_t tap_rows[9]; int64_t a_rows;
+    float alpha;
+    const float* bias; const float* col_scale;
+    const void* R; int64_t ldr, sr0, sr1; int32_t dtype_r;
+    int32_t act;
+    int32_t epi;
+    const float* norm_a; const float* norm_b; int64_t sna0, snb0;
+    float eps, inv_t, diag_add; int32_t cos_normalized;
+    int32_t rowmap, pad_h, pad_w, seg_in, seg_out, seg_off;
+    int32_t backend;
+} rb_gemm_args;
+int romab200_gemm(const rb_gemm_args* args, void* stream);
+
+/* LayerNorm over the last dim (nn.LayerNorm in block.py:50 / dinov2.py:88): y = (x-mu)/sqrt(var+eps)*g + b */
+typedef struct {
+    const void* x; void* y; const float* gamma; const float* beta;
+    int64_t rows; int32_t cols; int64_t ldx, ldy; int32_t dtype_x, dtype_y; float eps;
+} rb_layernorm_args;
+int romab200_layernorm(const rb_layernorm_args* args, void* stream);
+
+/* In-place row softmax of attention scores: s = softmax(scale * s) over `cols` (SDPA, attention.py:59) */
+typedef struct { void* s; int64_t rows; int32_t cols; int64_t lds; int32_t dtype; float scale; } rb_softmax_args;
+int romab200_softmax_rows(const rb_softmax_args* args, void* stream);
+
+/* L2 norm of every row: out[r] = ||x[r,:]||  (CosKernel, matcher.py:192-194) */
+typedef struct { const void* x; float* out; int64_t rows; int32_t cols; int64_t ldx; int32_t dtype; } rb_rownorm_args;
+int romab200_row_norms(const rb_rownorm_args* args, void* stream);
+
+/* Strided 2-D copy / cast: dst[r, c] = (dst_dtype) src[r, c] * scale[r]  (scale may be NULL) */
+typedef struct {
+    const void* src; void* dst; int64_t rows; int32_t cols; int64_t lds, ldd; int32_t dtype_src, dtype_dst;
+    const float* row_scale; int32_t row_scale_reciprocal;
+} rb_copy2d_args;
+int romab200_copy2d(const rb_copy2d_args* args, void* stream);
+
+/* fp16 hi/lo operand split for fp32-class accuracy on the f16 tensor pipe:
+ * dst[r, 0:C] = hi, dst[r, C:2C] = lo (or hi), dst[r, 2C:3C] = hi (or lo) of x[r,:]/scale[r]
+ * layout A: [hi | lo | hi], layout B: [hi | hi | lo]  so that A'.B'^T = hi.hi + lo.hi + hi.lo */
+typedef struct {
+    const float* x; void* dst; int64_t rows; int32_t cols; int64_t ldx, ldd; const float* row_norm;
+    int32_t layout_b;
+} rb_split_args;
+int romab200_split_f16x3(const rb_split_args* args, void* stream);
+
+/* ---- VGG19-BN pieces that are not GEMMs (encoders.py:17-27) ------------------------------------ */
+/* First conv (3 -> 64) + folded BN + ReLU, NCHW fp32 image -> zero-padded NHWC [B,H+2,W+2,64] */
+typedef struct {
+    const float* image; void* out; const float* weight /* [64][27] folded */; const float* bias /* [64] */;
+    int32_t batch, height, width, cout; int32_t dtype_out;
+} rb_conv_first_args;
+int romab200_conv3x3_first(const rb_conv_first_args* args, void* stream);
+/* 2x2/2 max-pool between zero-padded NHWC maps: [B,H+2,W+2,C] -> [B,H/2+2,W/2+2,C] */
+typedef struct { const void* in; void* out; int32_t batch, height, width, channels, dtype; } rb_maxpool_args;
+int romab200_maxpool2x2_padded(const rb_maxpool_args* args, void* stream);
+
+/* ---- DINOv2 tokenisation (dinov2.py:192-201, patch_embed.py:69-82) ------------------------------ */
+/* im2col of non-overlapping 14x14 patches: NCHW fp32 image -> [B*hp*wp, ldo] rows of (c,ky,kx) */
+typedef struct { const float* image; void* out; int32_t batch, height, width, patch; int64_t ldo; int32_t dtype_out; } rb_im2col_args;
+int romab200_im2col_patch(const rb_im2col_args* args, void* stream);
+/* tokens[b,0,:] = cls + pos[0]; tokens[b,1+p,:] = patch[b,p,:] + pos[1+p]   (fp32 residual stream) */
+typedef struct { const float* patch; const float* cls; const float* pos; float* tokens; int32_t batch, npatch, dim; } rb_tokens_args;
+int romab200_assemble_tokens(const rb_tokens_args* args, void* stream);
+
+/* ---- GP posterior (matcher.py:291-323): batched Cholesky + solves --------------------------------
+ * W is a batch of workspaces [n + nrhs, n] (row-major, pitch ldw): rows 0..n-1 hold the SPD matrix
+ * K_yy + sigma*I (lower triangle is read), rows n.. hold F^T ([nrhs, n]).  On return rows n.. hold
+ * X^T where (K_yy + sigma I) X = F, i.e. alpha^T, ready to be the [N,K] operand of mu = K_xy @ alpha.
+ * Replaces torch.linalg.cholesky + torch.cholesky_solve (matcher.py:307-308). */
+typedef struct { float* W; int32_t n, nrhs, batch; int64_t ldw, stride; } rb_gp_solve_args;
+int romab200_gp_solve(const rb_gp_solve_args* args, void* stream);
+/* ---- classifier head -> coarse flow (utils.py:300-322) ------------------------------------------
+ * logits [rows, ldl] fp32/16 with 4096 anchor logits followed by the certainty logit; writes
+ * state[row] = (flow_x, flow_y, certainty_logit). */
+typedef struct { const void* logits; float* state; int64_t rows; int64_t ldl; int32_t res; int32_t dtype; } rb_cls_args;
+int romab200_cls_to_flow_refine(const rb_cls_args* args, void* stream);
+
+/* ---- ConvRefiner (matcher.py:124-179) ------------------------------------------------------------
+ * feat: projected features of all encoder images [n_img, h, w, ldf] (channels-last, `cf` channels).
+ * For decoder item i the query image is `i` and the support image is (i + y_shift) % n_img.
+ * state: [D, h, w, 3] = (flow_x, flow_y, certainty_logit) fp32.
+ * prologue writes d[D,h,w,ldd] = [x | grid_sample(y, flow) | disp_emb(40/32*sf*(flow-grid)) | local_corr | 0-pad]
+ *   (matcher.py:132-168; local correlation per local_correlation.py:77-142 / local_corr.local_corr) */
+typedef struct {
+    const void* feat; int64_t ldf; int32_t n_img, y_shift;
+    const float* state; void* d; int64_t ldd;
+    int32_t D, h, w, cf, emb, radius; int32_t dtype;
+    const float* emb_weight /* [emb][2] */; const float* emb_bias; float disp_scale;
+    const float* grid_x; const float* grid_y;   /* linspace(-1+1/w, 1-1/w, w), linspace(-1+1/h, 1-1/h, h) (matcher.py:136-143) */
+    const float* win_x; const float* win_y;     /* linspace(-2r/w, 2r/w, 2r+1), linspace(-2r/h, 2r/h, 2r+1) (local_correlation.py:93-103) */
+} rb_refiner_prologue_args;
+int romab200_refiner_prologue(const rb_refiner_prologue_args* args, void* stream);
+
+/* Stand-alone local correlation with the reference wheel's semantics (local_correlation.py:22-35):
+ * corr[b, p, k] = sum_c f0[b,p,c] * bilinear(f1[b], flow[b,p] + window[k])  (f0 already scaled by caller or
+ * `scale` applied here), zero padding, k = (dy+r)*(2r+1) + (dx+r).  out pitch ldo (channels-last slice). */
+typedef struct {
+    const void* f0; const void* f1; int64_t ldf0, ldf1; int64_t f0_img_stride, f1_img_stride;
+    const float* flow; int64_t ldflow; void* out; int64_t ldo;
+    int32_t batch, h, w, c, radius; float scale; int32_t dtype_f, dtype_out;
+    int32_t n_img, y_shift;   /* f1 image of item i = (i + y_shift) % n_img ; f0 image = i */
+    const float* win_x; const float* win_y;   /* window offsets in normalised coordinates, 2r+1 each */
+} rb_local_corr_args;
+int romab200_local_corr(const rb_local_corr_args* args, void* stream);
+
+/* depthwise 5x5 conv (pad 2) + folded BN + ReLU on channels-last maps (create_block conv1+norm+relu,
+ * matcher.py:106-120).  weight [25][ldw] fp32 (tap-major), bias [C] */
+typedef struct {
+    const void* in; void* out; int64_t ldi, ldo; const float* weight; int64_t ldw; const float* bias;
+    int32_t batch, h, w, c; int32_t dtype;
+} rb_dwconv_args;
+int romab200_dwconv5x5_relu(const rb_dwconv_args* args, void* stream);
+
+/* out_conv (fp32 1x1, C -> 3) + flow/certainty update (matcher.py:177-179, 496-506):
+ * state[...,0] += scale_x * o0 ; state[...,1] += scale_y * o1 ; state[...,2] += o2 */
+typedef struct {
+    const void* d; int64_t ldd; const float* weight /* [3][ldw] */; int64_t ldw; const float* bias;
+    float* state; int64_t rows; int32_t c; float scale_x, scale_y; int32_t dtype; float* delta_out /* optional [rows,3] */;
+} rb_refiner_tail_args;
+int romab200_refiner_tail(const rb_refiner_tail_args* args, void* stream);
+
+/* bilinear resize, align_corners=False, no antialias (F.interpolate, matcher.py:424-435,513-523) of a
+ * channels-last fp32 map [B, hi, wi, c] -> [B, ho, wo, c] */
+typedef struct { const float* in; float* out; int32_t batch, hi, wi, ho, wo, c; } rb_resize_args;
+int romab200_bilinear_resize(const rb_resize_args* args, void* stream);
+
+/* match() epilogue (matcher.py:839-850, 891-927): certainty attenuation by the stride-16 logit, sigmoid,
+ * out-of-range mask, clamp, identity grids and the symmetric concat.
+ * state [D,H,W,3]; coarse_state [D,hc,wc,3] = the stride-16 state (NULL = no attenuation); warp [b,H,W*(sym?2:1),4]; cert [b,H,W*(sym?2:1)] */
+typedef struct {
+    const float* state; const float* coarse_state; int32_t hc, wc;
+    float* warp; float* cert; int32_t b, H, W, symmetric;
+    const float* grid_x; const float* grid_y;   /* pixel-centre linspaces of length W and H (matcher.py:904-912) */
+} rb_match_epilogue_args;
+int romab200_match_epilogue(const rb_match_epilogue_args* args, void* stream);
+
+/* sample(): Gaussian KDE density (kde.py:4-12) without materialising the NxN matrix.
+ * x [n,4] fp32; density[i] = sum_j exp(-||h(x_i)-h(x_j)||^2 / (2 std^2)), h = fp16 rounding when half != 0 */
+typedef struct { const float* x; float* density; int32_t n; float std; int32_t half; } rb_kde_args;
+int romab200_kde_density(const rb_kde_args* args, void* stream);
+
+/* transpose a batched strided 2-D matrix: dst[b][c][r] = src[b][r][c]  (V^T for the PV product) */
+typedef struct {
+    const void* src; void* dst; int32_t rows, cols; int64_t lds, ldd; int32_t batch0, batch1;
+    int64_t ss0, ss1, sd0, sd1; int32_t dtype;
+} rb_transpose_args;
+int romab200_transpose(const rb_transpose_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROMAB200_H */

@@ -1,0 +1,234 @@
+// Row-wise / element-wise kernels: LayerNorm, softmax, row norms, casts, fp16 hi/lo split,
+// DINOv2 tokenisation, batched transpose.  All HBM-bound; one warp (or block) per row, 16-byte
+// vector accesses where the pitch allows.
+#include "common.cuh"
+
+namespace rb {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, two-pass (mean, then centred variance) in fp32 like ATen's CPU kernel.
+// ------------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void layernorm_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ g,
+                                 const float* __restrict__ b, int64_t rows, int cols, int64_t ldx, int64_t ldy, float eps) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (row >= rows) return;
+    int lane = threadIdx.x & 31;
+    const TI* xr = x + row * ldx;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += to_f(xr[c]);
+    float mean = warp_sum(s) / cols;
+    float v = 0.f;
+    for (int c = lane; c < cols; c += 32) { float d = to_f(xr[c]) - mean; v += d * d; }
+    float rstd = rsqrtf(warp_sum(v) / cols + eps);
+    TO* yr = y + row * ldy;
+    for (int c = lane; c < cols; c += 32) yr[c] = from_f<TO>((to_f(xr[c]) - mean) * rstd * g[c] + b[c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax over rows (attention scores), in place: one block of 256 threads per row
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void softmax_rows_kernel(T* __restrict__ s, int64_t rows, int cols, int64_t lds, float scale) {
+    __shared__ float red[8];
+    int64_t row = blockIdx.x;
+    T* sr = s + row * lds;
+    int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float m = -INFINITY;
+    for (int c = tid; c < cols; c += 256) m = fmaxf(m, to_f(sr[c]) * scale);
+    m = warp_max(m);
+    if (lane == 0) red[wid] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int c = tid; c < cols; c += 256) sum += expf(to_f(sr[c]) * scale - m);
+    sum = warp_sum(sum);
+    if (lane == 0) red[wid] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += red[i];
+    float inv = 1.0f / sum;
+    for (int c = tid; c < cols; c += 256) sr[c] = from_f<T>(expf(to_f(sr[c]) * scale - m) * inv);
+}
+
+template <typename T>
+__global__ void row_norms_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t rows, int cols, int64_t ldx) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (row >= rows) return;
+    int lane = threadIdx.x & 31;
+    const T* xr = x + row * ldx;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) { float v = to_f(xr[c]); s += v * v; }
+    s = warp_sum(s);
+    if (lane == 0) out[row] = sqrtf(s);
+}
+
+__global__ void copy2d_kernel(const void* __restrict__ src, void* __restrict__ dst, int64_t rows, int cols, int64_t lds,
+                              int64_t ldd, int ds, int dd, const float* __restrict__ row_scale, int recip) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = rows * cols;
+    for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = idx / cols; int c = (int)(idx - r * cols);
+        float v = load_any(src, r * lds + c, ds);
+        if (row_scale) v = recip ? v / row_scale[r] : v * row_scale[r];
+        store_any(dst, r * ldd + c, dd, v);
+    }
+}
+
+// x / norm -> fp16 hi and lo parts laid out [hi|lo|hi] (A operand) or [hi|hi|lo] (B operand)
+__global__ void split_f16x3_kernel(const float* __restrict__ x, __half* __restrict__ dst, int64_t rows, int cols,
+                                   int64_t ldx, int64_t ldd, const float* __restrict__ norm, int layout_b) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = rows * cols;
+    for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = idx / cols; int c = (int)(idx - r * cols);
+        float v = x[r * ldx + c];
+        if (norm) v = v / norm[r];
+        __half hi = __float2half_rn(v);
+        __half lo = __float2half_rn(v - __half2float(hi));
+        __half* d = dst + r * ldd;
+        d[c] = hi;
+        d[cols + c] = layout_b ? hi : lo;
+        d[2 * cols + c] = layout_b ? lo : hi;
+    }
+}
+
+// im2col of PxP non-overlapping patches: out[(b*hp+py)*wp+px][c*P*P + ky*P + kx] = img[b][c][py*P+ky][px*P+kx]
+// (same (c,ky,kx) order as Conv2d weight.flatten(1), patch_embed.py:69-82)
+template <typename TO>
+__global__ void im2col_patch_kernel(const float* __restrict__ img, TO* __restrict__ out, int B, int H, int W, int P, int64_t ldo) {
+    int hp = H / P, wp = W / P, kk = 3 * P * P;
+    int64_t total = (int64_t)B * hp * wp * kk;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int k = (int)(idx % kk); int64_t row = idx / kk;
+        int px = (int)(row % wp); int py = (int)((row / wp) % hp); int b = (int)(row / ((int64_t)wp * hp));
+        int c = k / (P * P), r = k % (P * P), ky = r / P, kx = r % P;
+        float v = img[(((int64_t)b * 3 + c) * H + (py * P + ky)) * W + (px * P + kx)];
+        out[row * ldo + k] = from_f<TO>(v);
+    }
+}
+
+__global__ void assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+                                       const float* __restrict__ pos, float* __restrict__ tok, int B, int np, int dim) {
+    int64_t total = (int64_t)B * (np + 1) * dim;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(idx % dim); int64_t r = idx / dim;
+        int t = (int)(r % (np + 1)); int b = (int)(r / (np + 1));
+        float v = t == 0 ? cls[c] : patch[((int64_t)b * np + (t - 1)) * dim + c];
+        tok[idx] = v + pos[(int64_t)t * dim + c];
+    }
+}
+
+// batched transpose through a 32x33 shared tile
+template <typename T>
+__global__ void transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, int rows, int cols, int64_t lds, int64_t ldd,
+                                 int batch1, int64_t ss0, int64_t ss1, int64_t sd0, int64_t sd1) {
+    __shared__ T tile[32][33];
+    int z = blockIdx.z, z0 = z / batch1, z1 = z % batch1;
+    const T* s = src + z0 * ss0 + z1 * ss1;
+    T* d = dst + z0 * sd0 + z1 * sd1;
+    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = s[(int64_t)r * lds + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) d[(int64_t)c * ldd + r] = tile[threadIdx.x][i];
+    }
+}
+
+static inline int grid_for(int64_t total, int block, int cap = 148 * 32) {
+    int64_t g = (total + block - 1) / block;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" int romab200_layernorm(const rb_layernorm_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->rows > 0 && a->cols > 0, "layernorm: empty input");
+    int wpb = 8;
+    dim3 grid((unsigned)((a->rows + wpb - 1) / wpb));
+#define LN(TI, TO) layernorm_kernel<TI, TO><<<grid, wpb * 32, 0, st>>>((const TI*)a->x, (TO*)a->y, a->gamma, a->beta, a->rows, a->cols, a->ldx, a->ldy, a->eps)
+    if (a->dtype_x == RB_F32 && a->dtype_y == RB_F32) LN(float, float);
+    else if (a->dtype_x == RB_F32 && a->dtype_y == RB_F16) LN(float, __half);
+    else if (a->dtype_x == RB_F32 && a->dtype_y == RB_BF16) LN(float, __nv_bfloat16);
+    else RB_REQUIRE(false, "layernorm: unsupported dtypes %d -> %d", a->dtype_x, a->dtype_y);
+#undef LN
+    return check_launch("layernorm");
+}
+
+extern "C" int romab200_softmax_rows(const rb_softmax_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->rows > 0 && a->cols > 0 && a->rows < (1ll << 31), "softmax: bad shape");
+    if (a->dtype == RB_F32) softmax_rows_kernel<float><<<(unsigned)a->rows, 256, 0, st>>>((float*)a->s, a->rows, a->cols, a->lds, a->scale);
+    else if (a->dtype == RB_F16) softmax_rows_kernel<__half><<<(unsigned)a->rows, 256, 0, st>>>((__half*)a->s, a->rows, a->cols, a->lds, a->scale);
+    else softmax_rows_kernel<__nv_bfloat16><<<(unsigned)a->rows, 256, 0, st>>>((__nv_bfloat16*)a->s, a->rows, a->cols, a->lds, a->scale);
+    return check_launch("softmax_rows");
+}
+
+extern "C" int romab200_row_norms(const rb_rownorm_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->rows > 0 && a->cols > 0, "row_norms: empty input");
+    dim3 grid((unsigned)((a->rows + 7) / 8));
+    if (a->dtype == RB_F32) row_norms_kernel<float><<<grid, 256, 0, st>>>((const float*)a->x, a->out, a->rows, a->cols, a->ldx);
+    else if (a->dtype == RB_F16) row_norms_kernel<__half><<<grid, 256, 0, st>>>((const __half*)a->x, a->out, a->rows, a->cols, a->ldx);
+    else row_norms_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->x, a->out, a->rows, a->cols, a->ldx);
+    return check_launch("row_norms");
+}
+
+extern "C" int romab200_copy2d(const rb_copy2d_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->rows > 0 && a->cols > 0, "copy2d: empty input");
+    copy2d_kernel<<<grid_for(a->rows * a->cols, 256), 256, 0, st>>>(a->src, a->dst, a->rows, a->cols, a->lds, a->ldd,
+                                                                   a->dtype_src, a->dtype_dst, a->row_scale, a->row_scale_reciprocal);
+    return check_launch("copy2d");
+}
+
+extern "C" int romab200_split_f16x3(const rb_split_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->rows > 0 && a->cols > 0 && a->ldd >= 3 * a->cols, "split_f16x3: bad shape");
+    split_f16x3_kernel<<<grid_for(a->rows * a->cols, 256), 256, 0, st>>>(a->x, (__half*)a->dst, a->rows, a->cols, a->ldx, a->ldd,
+                                                                        a->row_norm, a->layout_b);
+    return check_launch("split_f16x3");
+}
+
+extern "C" int romab200_im2col_patch(const rb_im2col_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->height % a->patch == 0 && a->width % a->patch == 0, "im2col: %dx%d not a multiple of patch %d", a->height, a->width, a->patch);
+    int64_t total = (int64_t)a->batch * (a->height / a->patch) * (a->width / a->patch) * 3 * a->patch * a->patch;
+    int g = grid_for(total, 256);
+    if (a->dtype_out == RB_F32) im2col_patch_kernel<float><<<g, 256, 0, st>>>(a->image, (float*)a->out, a->batch, a->height, a->width, a->patch, a->ldo);
+    else if (a->dtype_out == RB_F16) im2col_patch_kernel<__half><<<g, 256, 0, st>>>(a->image, (__half*)a->out, a->batch, a->height, a->width, a->patch, a->ldo);
+    else im2col_patch_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(a->image, (__nv_bfloat16*)a->out, a->batch, a->height, a->width, a->patch, a->ldo);
+    return check_launch("im2col_patch");
+}
+
+extern "C" int romab200_assemble_tokens(const rb_tokens_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t total = (int64_t)a->batch * (a->npatch + 1) * a->dim;
+    assemble_tokens_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->patch, a->cls, a->pos, a->tokens, a->batch, a->npatch, a->dim);
+    return check_launch("assemble_tokens");
+}
+
+extern "C" int romab200_transpose(const rb_transpose_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int b0 = a->batch0 > 0 ? a->batch0 : 1, b1 = a->batch1 > 0 ? a->batch1 : 1;
+    dim3 grid((a->cols + 31) / 32, (a->rows + 31) / 32, b0 * b1), block(32, 8);
+    RB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "transpose: grid too large");
+    if (a->dtype == RB_F32)
+        transpose_kernel<float><<<grid, block, 0, st>>>((const float*)a->src, (float*)a->dst, a->rows, a->cols, a->lds, a->ldd, b1, a->ss0, a->ss1, a->sd0, a->sd1);
+    else
+        transpose_kernel<uint16_t><<<grid, block, 0, st>>>((const uint16_t*)a->src, (uint16_t*)a->dst, a->rows, a->cols, a->lds, a->ldd, b1, a->ss0, a->ss1, a->sd0, a->sd1);
+    return check_launch("transpose");
+}

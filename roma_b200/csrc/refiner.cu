@@ -1,0 +1,502 @@
+// Coarse-to-fine refinement kernels (romatch/models/matcher.py:124-179, 395-527, 839-927;
+// romatch/utils/local_correlation.py:77-142; romatch/utils/utils.py:300-322).
+//
+// Layout: every feature map is channels-last [img, h, w, C] with an explicit pitch; the flow and the
+// certainty logit travel together as a 3-channel fp32 "state" map [D, h, w, 3] = (x, y, logit).
+// All kernels here are gather / streaming kernels (HBM- or L2-bound); one warp per pixel with lanes over
+// channels, so every global access is a contiguous run of the channel vector.
+#include "common.cuh"
+
+namespace rb {
+
+// --------------------------------------------------------------------------------------------------
+// helpers
+// --------------------------------------------------------------------------------------------------
+template <typename T> struct Vec16;   // 16-byte vector of T
+template <> struct Vec16<float> { static constexpr int N = 4; };
+template <> struct Vec16<__half> { static constexpr int N = 8; };
+template <> struct Vec16<__nv_bfloat16> { static constexpr int N = 8; };
+
+template <typename T>
+__device__ __forceinline__ void load_vec(const T* p, float* out) {
+    constexpr int N = Vec16<T>::N;
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = to_f(e[i]);
+}
+
+// sum v[i] over the warp for all 32 i at once: afterwards lane l returns the total of v[l] (31 shuffles)
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#define RB_STAGE(OFF, HALF)                                                    \
+    {                                                                          \
+        bool up = lane & OFF;                                                  \
+        _Pragma("unroll") for (int i = 0; i < HALF; ++i) {                     \
+            float send = up ? v[i] : v[i + HALF];                              \
+            float keep = up ? v[i + HALF] : v[i];                              \
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);             \
+        }                                                                      \
+    }
+    RB_STAGE(16, 16) RB_STAGE(8, 8) RB_STAGE(4, 4) RB_STAGE(2, 2) RB_STAGE(1, 1)
+#undef RB_STAGE
+    return v[0];
+}
+
+// --------------------------------------------------------------------------------------------------
+// local correlation for one pixel by one warp.
+// D[j][i] = scale * <f0, f1[by+j, bx+i]> on the (2R+2)^2 integer neighbourhood (zero outside the image),
+// then every window sample k is the bilinear blend of four D entries with the weights grid_sample would
+// use for the coordinate flow + window[k] (all (2R+1)^2 samples sit on a unit pixel lattice).
+// --------------------------------------------------------------------------------------------------
+template <typename T, int R, typename TO>
+__device__ __forceinline__ void local_corr_warp(const T* __restrict__ f0, const T* __restrict__ f1, int64_t ldf1, float fx, float fy,
+                                                int h, int w, int c, float scale, const float* __restrict__ winx,
+                                                const float* __restrict__ winy, float* __restrict__ dtab, TO* __restrict__ out, int lane) {
+    constexpr int S = 2 * R + 2, P = S * S, K1 = 2 * R + 1, K = K1 * K1;
+    constexpr int VN = Vec16<T>::N;
+    constexpr int MAXCH = 512 / (32 * VN);      // channel chunks per lane (c <= 512)
+    const float cx = ((fx + 1.f) * w - 1.f) * 0.5f, cy = ((fy + 1.f) * h - 1.f) * 0.5f;
+    const int bx = (int)floorf(cx) - R, by = (int)floorf(cy) - R;
+
+    float f0r[MAXCH][VN];
+#pragma unroll
+    for (int t = 0; t < MAXCH; ++t) {
+        int c0 = (t * 32 + lane) * VN;
+        if (c0 < c) load_vec<T>(f0 + c0, f0r[t]);
+        else {
+#pragma unroll
+            for (int i = 0; i < VN; ++i) f0r[t][i] = 0.f;
+        }
+    }
+    for (int g = 0; g < (P + 31) / 32; ++g) {
+        float part[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) part[q] = 0.f;
+#pragma unroll
+        for (int t = 0; t < MAXCH; ++t) {
+            int c0 = (t * 32 + lane) * VN;
+            if (c0 < c) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    int p = g * 32 + q;
+                    int i = p % S, j = p / S;
+                    int xx = bx + i, yy = by + j;
+                    if (p < P && xx >= 0 && xx < w && yy >= 0 && yy < h) {     // warp-uniform
+                        float v[VN];
+                        load_vec<T>(f1 + ((int64_t)yy * w + xx) * ldf1 + c0, v);
+                        float s = 0.f;
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) s = fmaf(f0r[t][e], v[e], s);
+                        part[q] += s;
+                    }
+                }
+            }
+        }
+        float tot = warp_transpose_reduce(part, lane);
+        if (g * 32 + lane < P) dtab[g * 32 + lane] = tot * scale;
+    }
+    __syncwarp();
+    for (int k = lane; k < K; k += 32) {
+        int dy = k / K1, dx = k - dy * K1;
+        float xk = fx + winx[dx], yk = fy + winy[dy];
+        float ix = ((xk + 1.f) * w - 1.f) * 0.5f, iy = ((yk + 1.f) * h - 1.f) * 0.5f;
+        float x0 = floorf(ix), y0 = floorf(iy);
+        float wx1 = ix - x0, wx0 = (x0 + 1.f) - ix, wy1 = iy - y0, wy0 = (y0 + 1.f) - iy;
+        int ti = (int)x0 - bx, tj = (int)y0 - by;
+        int ti0 = min(max(ti, 0), S - 1), ti1 = min(max(ti + 1, 0), S - 1);
+        int tj0 = min(max(tj, 0), S - 1), tj1 = min(max(tj + 1, 0), S - 1);
+        float v = dtab[tj0 * S + ti0] * (wx0 * wy0) + dtab[tj0 * S + ti1] * (wx1 * wy0) +
+                  dtab[tj1 * S + ti0] * (wx0 * wy1) + dtab[tj1 * S + ti1] * (wx1 * wy1);
+        out[k] = from_f<TO>(v);
+    }
+    __syncwarp();
+}
+
+// --------------------------------------------------------------------------------------------------
+// ConvRefiner prologue: d = [x | grid_sample(y, flow) | disp_emb | local_corr]   (matcher.py:132-168)
+// --------------------------------------------------------------------------------------------------
+struct PrologueParams {
+    const void* feat; int64_t ldf; int n_img, y_shift;
+    const float* state; void* d; int64_t ldd;
+    int D, h, w, cf, emb;
+    const float* emb_w; const float* emb_b; float disp_scale;
+    const float* gx; const float* gy; const float* winx; const float* winy;
+};
+
+template <typename T, int R>
+__global__ void __launch_bounds__(128) refiner_prologue_kernel(const PrologueParams p) {
+    constexpr int S = 2 * R + 2;
+    __shared__ float dtab_all[4][R > 0 ? S * S : 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t pix = (int64_t)blockIdx.x * 4 + wid;
+    const int64_t hw = (int64_t)p.h * p.w;
+    if (pix >= p.D * hw) return;
+    const int item = (int)(pix / hw);
+    const int rem = (int)(pix - item * hw);
+    const int y = rem / p.w, x = rem - y * p.w;
+    const float fx = p.state[pix * 3 + 0], fy = p.state[pix * 3 + 1];
+    const T* feat = (const T*)p.feat;
+    const T* xrow = feat + ((int64_t)item * hw + rem) * p.ldf;
+    const T* yimg = feat + (int64_t)((item + p.y_shift) % p.n_img) * hw * p.ldf;
+    T* drow = (T*)p.d + pix * p.ldd;
+    const int cf = p.cf;
+
+    // grid_sample(y, flow): bilinear, zeros padding, align_corners=False
+    const float ix = ((fx + 1.f) * p.w - 1.f) * 0.5f, iy = ((fy + 1.f) * p.h - 1.f) * 0.5f;
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const float wx1 = ix - x0f, wx0 = (x0f + 1.f) - ix, wy1 = iy - y0f, wy0 = (y0f + 1.f) - iy;
+    const bool vx0 = x0 >= 0 && x0 < p.w, vx1 = x0 + 1 >= 0 && x0 + 1 < p.w;
+    const bool vy0 = y0 >= 0 && y0 < p.h, vy1 = y0 + 1 >= 0 && y0 + 1 < p.h;
+    const T* p00 = yimg + ((int64_t)y0 * p.w + x0) * p.ldf;
+    const T* p01 = p00 + p.ldf;
+    const T* p10 = p00 + (int64_t)p.w * p.ldf;
+    const T* p11 = p10 + p.ldf;
+    for (int c = lane; c < cf; c += 32) {
+        drow[c] = xrow[c];
+        float v = 0.f;
+        if (vy0 && vx0) v += to_f(p00[c]) * (wx0 * wy0);
+        if (vy0 && vx1) v += to_f(p01[c]) * (wx1 * wy0);
+        if (vy1 && vx0) v += to_f(p10[c]) * (wx0 * wy1);
+        if (vy1 && vx1) v += to_f(p11[c]) * (wx1 * wy1);
+        drow[cf + c] = from_f<T>(v);
+    }
+    // displacement embedding: 1x1 conv 2 -> emb on disp_scale * (flow - identity grid)   (matcher.py:135-148)
+    const float ddx = p.disp_scale * (fx - p.gx[x]), ddy = p.disp_scale * (fy - p.gy[y]);
+    for (int e = lane; e < p.emb; e += 32)
+        drow[2 * cf + e] = from_f<T>(p.emb_w[2 * e] * ddx + p.emb_w[2 * e + 1] * ddy + p.emb_b[e]);
+    if constexpr (R > 0)
+        local_corr_warp<T, R, T>(xrow, yimg, p.ldf, fx, fy, p.h, p.w, cf, rsqrtf((float)cf), p.winx, p.winy, dtab_all[wid],
+                                 drow + 2 * cf + p.emb, lane);
+}
+
+// stand-alone local correlation (the reference wheel's operator boundary, local_correlation.py:22-35)
+struct LocalCorrParams {
+    const void* f0; const void* f1; int64_t ldf0, ldf1, f0_img_stride, f1_img_stride;
+    const float* flow; int64_t ldflow; void* out; int64_t ldo;
+    int batch, h, w, c; float scale; int n_img, y_shift;
+    const float* winx; const float* winy;
+};
+template <typename T, int R, typename TO>
+__global__ void __launch_bounds__(128) local_corr_kernel(const LocalCorrParams p) {
+    constexpr int S = 2 * R + 2;
+    __shared__ float dtab_all[4][S * S];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t pix = (int64_t)blockIdx.x * 4 + wid;
+    const int64_t hw = (int64_t)p.h * p.w;
+    if (pix >= p.batch * hw) return;
+    const int item = (int)(pix / hw);
+    const int rem = (int)(pix - item * hw);
+    const float fx = p.flow[pix * p.ldflow + 0], fy = p.flow[pix * p.ldflow + 1];
+    const T* f0 = (const T*)p.f0 + item * p.f0_img_stride + (int64_t)rem * p.ldf0;
+    const T* f1 = (const T*)p.f1 + (int64_t)((item + p.y_shift) % p.n_img) * p.f1_img_stride;
+    local_corr_warp<T, R, TO>(f0, f1, p.ldf1, fx, fy, p.h, p.w, p.c, p.scale, p.winx, p.winy, dtab_all[wid],
+                              (TO*)p.out + pix * p.ldo, lane);
+}
+
+// --------------------------------------------------------------------------------------------------
+// depthwise 5x5 + folded BN + ReLU, channels-last.  Block = 8 output rows x 16 output columns x 32 channels;
+// the (8+4)x(16+4)x32 input tile is staged in shared memory as fp32; each thread owns one channel of one
+// output row and slides along x with the 25 weights in registers (100 LDS + 400 FMA per 16 outputs).
+// --------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv5x5_relu_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t ldi, int64_t ldo,
+                                                             const float* __restrict__ wgt, int64_t ldw, const float* __restrict__ bias,
+                                                             int H, int W, int C, int tiles_x) {
+    constexpr int TH = 8, TW = 16, CH = 32;
+    __shared__ float tile[TH + 4][TW + 4][CH];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int c0 = blockIdx.y * CH, b = blockIdx.z;
+    const int x0 = tx * TW, y0 = ty * TH;
+    const int c = c0 + lane;
+    const bool cok = c < C;
+    const T* inb = in + (int64_t)b * H * W * ldi;
+    for (int pidx = wid; pidx < (TH + 4) * (TW + 4); pidx += 8) {
+        int py = pidx / (TW + 4), px = pidx % (TW + 4);
+        int yy = y0 + py - 2, xx = x0 + px - 2;
+        float v = 0.f;
+        if (cok && yy >= 0 && yy < H && xx >= 0 && xx < W) v = to_f(inb[((int64_t)yy * W + xx) * ldi + c]);
+        tile[py][px][lane] = v;
+    }
+    float wr[25];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) wr[t] = cok ? wgt[(int64_t)t * ldw + c] : 0.f;
+    const float bv = cok ? bias[c] : 0.f;
+    __syncthreads();
+    float acc[TW];
+#pragma unroll
+    for (int i = 0; i < TW; ++i) acc[i] = bv;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+        for (int px = 0; px < TW + 4; ++px) {
+            float v = tile[wid + ky][px][lane];
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+                int ox = px - kx;
+                if (ox >= 0 && ox < TW) acc[ox] = fmaf(wr[ky * 5 + kx], v, acc[ox]);
+            }
+        }
+    }
+    const int yy = y0 + wid;
+    if (!cok || yy >= H) return;
+    T* ob = out + ((int64_t)b * H * W + (int64_t)yy * W) * ldo + c;
+#pragma unroll
+    for (int i = 0; i < TW; ++i)
+        if (x0 + i < W) ob[(int64_t)(x0 + i) * ldo] = from_f<T>(fmaxf(acc[i], 0.f));
+}
+
+// --------------------------------------------------------------------------------------------------
+// out_conv (C -> 3, fp32) + state update: one warp per pixel
+// --------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) refiner_tail_kernel(const T* __restrict__ d, int64_t ldd, const float* __restrict__ wgt, int64_t ldw,
+                                                           const float* __restrict__ bias, float* __restrict__ state, int64_t rows, int C,
+                                                           float sx, float sy, float* __restrict__ delta_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T* dr = d + row * ldd;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float v = to_f(dr[c]);
+        a0 = fmaf(v, wgt[c], a0);
+        a1 = fmaf(v, wgt[ldw + c], a1);
+        a2 = fmaf(v, wgt[2 * ldw + c], a2);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) {
+        a0 += bias[0]; a1 += bias[1]; a2 += bias[2];
+        if (delta_out) { delta_out[row * 3 + 0] = a0; delta_out[row * 3 + 1] = a1; delta_out[row * 3 + 2] = a2; }
+        state[row * 3 + 0] += sx * a0;
+        state[row * 3 + 1] += sy * a1;
+        state[row * 3 + 2] += a2;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// bilinear resize (align_corners=False, no antialias) of a small-channel fp32 map
+// src index: max(scale*(dst+0.5)-0.5, 0), scale = in/out (ATen area_pixel_compute_source_index)
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilinear_src(int dst, int in_size, int out_size, int& i0, int& i1, float& l1) {
+    float scale = (float)in_size / (float)out_size;
+    float s = scale * (dst + 0.5f) - 0.5f;
+    if (s < 0.f) s = 0.f;
+    i0 = (int)s;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = s - i0;
+}
+
+__global__ void bilinear_resize_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int hi, int wi, int ho, int wo, int C) {
+    int64_t total = (int64_t)B * ho * wo * C;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(idx % C); int64_t p = idx / C;
+        int xo = (int)(p % wo); int yo = (int)((p / wo) % ho); int b = (int)(p / ((int64_t)wo * ho));
+        int y0, y1, x0, x1; float ly, lx;
+        bilinear_src(yo, hi, ho, y0, y1, ly);
+        bilinear_src(xo, wi, wo, x0, x1, lx);
+        const float* s = in + (int64_t)b * hi * wi * C + c;
+        float v00 = s[((int64_t)y0 * wi + x0) * C], v01 = s[((int64_t)y0 * wi + x1) * C];
+        float v10 = s[((int64_t)y1 * wi + x0) * C], v11 = s[((int64_t)y1 * wi + x1) * C];
+        float hy = 1.f - ly, hx = 1.f - lx;
+        out[idx] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// cls_to_flow_refine (utils.py:300-322): one block per location
+// --------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) cls_to_flow_kernel(const T* __restrict__ logits, float* __restrict__ state, int64_t ldl, int res) {
+    __shared__ float smax[8]; __shared__ int sidx[8]; __shared__ float ssum[8];
+    const int C = res * res;
+    const int64_t row = blockIdx.x;
+    const T* l = logits + row * ldl;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float m = -INFINITY; int mi = 0x7fffffff;
+    for (int c = tid; c < C; c += 256) { float v = to_f(l[c]); if (v > m) { m = v; mi = c; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float om = __shfl_xor_sync(0xffffffffu, m, o); int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+    }
+    if (lane == 0) { smax[wid] = m; sidx[wid] = mi; }
+    __syncthreads();
+    m = smax[0]; mi = sidx[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) if (smax[i] > m || (smax[i] == m && sidx[i] < mi)) { m = smax[i]; mi = sidx[i]; }
+    float s = 0.f;
+    for (int c = tid; c < C; c += 256) s += expf(to_f(l[c]) - m);
+    s = warp_sum(s);
+    if (lane == 0) ssum[wid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += ssum[i];
+        int nb[5] = {mi - 1, mi, mi + 1, mi - res, mi + res};
+        float fx = 0.f, fy = 0.f, ps = 0.f;
+        const float step = 2.0f / res, first = -1.0f + 1.0f / res;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            int i = min(max(nb[j], 0), C - 1);
+            float pj = expf(to_f(l[i]) - m) / tot;
+            // anchor grid: linspace(-1+1/res, 1-1/res, res): x = c % res, y = c / res
+            float ax = first + step * (i % res), ay = first + step * (i / res);
+            fx += pj * ax; fy += pj * ay; ps += pj;
+        }
+        state[row * 3 + 0] = fx / ps;
+        state[row * 3 + 1] = fy / ps;
+        state[row * 3 + 2] = to_f(l[C]);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// match() epilogue (matcher.py:839-850, 891-927)
+// --------------------------------------------------------------------------------------------------
+__global__ void match_epilogue_kernel(const float* __restrict__ state, const float* __restrict__ coarse, int hc, int wc,
+                                      float* __restrict__ warp, float* __restrict__ cert, int b, int H, int W, int symmetric,
+                                      const float* __restrict__ gx, const float* __restrict__ gy) {
+    const int D = symmetric ? 2 * b : b;
+    int64_t total = (int64_t)D * H * W;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int x = (int)(idx % W); int y = (int)((idx / W) % H); int item = (int)(idx / ((int64_t)W * H));
+        float fx = state[idx * 3 + 0], fy = state[idx * 3 + 1], logit = state[idx * 3 + 2];
+        if (coarse) {
+            int y0, y1, x0, x1; float ly, lx;
+            bilinear_src(y, hc, H, y0, y1, ly);
+            bilinear_src(x, wc, W, x0, x1, lx);
+            const float* s = coarse + (int64_t)item * hc * wc * 3 + 2;      // certainty channel of the stride-16 state
+            float v00 = s[((int64_t)y0 * wc + x0) * 3], v01 = s[((int64_t)y0 * wc + x1) * 3];
+            float v10 = s[((int64_t)y1 * wc + x0) * 3], v11 = s[((int64_t)y1 * wc + x1) * 3];
+            float low = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+            low = 0.5f * low * (low < 0.f ? 1.f : 0.f);
+            logit -= low;
+        }
+        float c = 1.0f / (1.0f + expf(-logit));
+        if (fabsf(fx) > 1.f || fabsf(fy) > 1.f) c = 0.f;
+        fx = fminf(fmaxf(fx, -1.f), 1.f); fy = fminf(fmaxf(fy, -1.f), 1.f);
+        const int Wout = symmetric ? 2 * W : W;
+        const bool second = symmetric && item >= b;
+        const int ob = second ? item - b : item;
+        const int64_t o = ((int64_t)ob * H + y) * Wout + (second ? W + x : x);
+        float4 wv = second ? make_float4(fx, fy, gx[x], gy[y]) : make_float4(gx[x], gy[y], fx, fy);
+        *reinterpret_cast<float4*>(warp + o * 4) = wv;
+        cert[o] = c;
+    }
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+static inline unsigned grid1d(int64_t total, int block) {
+    int64_t g = (total + block - 1) / block;
+    int64_t cap = 148 * 64;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+extern "C" int romab200_refiner_prologue(const rb_refiner_prologue_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->cf > 0 && a->cf <= 512, "refiner_prologue: cf=%d", a->cf);
+    RB_REQUIRE(a->ldd >= 2 * a->cf + a->emb + (2 * a->radius + 1) * (2 * a->radius + 1) * (a->radius > 0), "refiner_prologue: ldd too small");
+    if (a->radius > 0) {
+        int vn = a->dtype == RB_F32 ? 4 : 8;
+        RB_REQUIRE(a->cf % vn == 0 && a->ldf % vn == 0 && ((uintptr_t)a->feat) % 16 == 0,
+                   "refiner_prologue: local correlation needs 16-byte aligned channel vectors (cf=%d ldf=%lld)", a->cf, (long long)a->ldf);
+        RB_REQUIRE(a->win_x && a->win_y, "refiner_prologue: window offsets missing");
+    }
+    PrologueParams p;
+    p.feat = a->feat; p.ldf = a->ldf; p.n_img = a->n_img; p.y_shift = a->y_shift; p.state = a->state; p.d = a->d; p.ldd = a->ldd;
+    p.D = a->D; p.h = a->h; p.w = a->w; p.cf = a->cf; p.emb = a->emb; p.emb_w = a->emb_weight; p.emb_b = a->emb_bias;
+    p.disp_scale = a->disp_scale; p.gx = a->grid_x; p.gy = a->grid_y; p.winx = a->win_x; p.winy = a->win_y;
+    int64_t pixels = (int64_t)a->D * a->h * a->w;
+    unsigned grid = (unsigned)((pixels + 3) / 4);
+#define LAUNCH(T, R) refiner_prologue_kernel<T, R><<<grid, 128, 0, st>>>(p)
+#define BYR(T)                                                                                        \
+    switch (a->radius) {                                                                              \
+        case 0: LAUNCH(T, 0); break; case 2: LAUNCH(T, 2); break; case 3: LAUNCH(T, 3); break;        \
+        case 7: LAUNCH(T, 7); break; default: RB_REQUIRE(false, "refiner_prologue: radius %d unsupported", a->radius); \
+    }
+    if (a->dtype == RB_F32) { BYR(float) } else if (a->dtype == RB_F16) { BYR(__half) } else { BYR(__nv_bfloat16) }
+#undef BYR
+#undef LAUNCH
+    return check_launch("refiner_prologue");
+}
+
+extern "C" int romab200_local_corr(const rb_local_corr_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->c > 0 && a->c <= 512, "local_corr: c=%d (max 512)", a->c);
+    int vn = a->dtype_f == RB_F32 ? 4 : 8;
+    RB_REQUIRE(a->c % vn == 0 && a->ldf0 % vn == 0 && a->ldf1 % vn == 0 && a->f0_img_stride % vn == 0 && a->f1_img_stride % vn == 0 &&
+               ((uintptr_t)a->f0) % 16 == 0 && ((uintptr_t)a->f1) % 16 == 0, "local_corr: channel vectors must be 16-byte aligned");
+    RB_REQUIRE(a->dtype_out == RB_F32 || a->dtype_out == a->dtype_f, "local_corr: output dtype must be fp32 or the feature dtype");
+    LocalCorrParams p;
+    p.f0 = a->f0; p.f1 = a->f1; p.ldf0 = a->ldf0; p.ldf1 = a->ldf1; p.f0_img_stride = a->f0_img_stride; p.f1_img_stride = a->f1_img_stride;
+    p.flow = a->flow; p.ldflow = a->ldflow; p.out = a->out; p.ldo = a->ldo; p.batch = a->batch; p.h = a->h; p.w = a->w; p.c = a->c;
+    p.scale = a->scale; p.n_img = a->n_img > 0 ? a->n_img : a->batch; p.y_shift = a->y_shift; p.winx = a->win_x; p.winy = a->win_y;
+    int64_t pixels = (int64_t)a->batch * a->h * a->w;
+    unsigned grid = (unsigned)((pixels + 3) / 4);
+#define LAUNCH(T, R, TO) local_corr_kernel<T, R, TO><<<grid, 128, 0, st>>>(p)
+#define BYR(T, TO)                                                                                    \
+    switch (a->radius) {                                                                              \
+        case 2: LAUNCH(T, 2, TO); break; case 3: LAUNCH(T, 3, TO); break; case 7: LAUNCH(T, 7, TO); break; \
+        default: RB_REQUIRE(false, "local_corr: radius %d unsupported (2, 3, 7)", a->radius);         \
+    }
+    if (a->dtype_f == RB_F32) { BYR(float, float) }
+    else if (a->dtype_f == RB_F16) { if (a->dtype_out == RB_F32) { BYR(__half, float) } else { BYR(__half, __half) } }
+    else { if (a->dtype_out == RB_F32) { BYR(__nv_bfloat16, float) } else { BYR(__nv_bfloat16, __nv_bfloat16) } }
+#undef BYR
+#undef LAUNCH
+    return check_launch("local_corr");
+}
+
+extern "C" int romab200_dwconv5x5_relu(const rb_dwconv_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int tiles_x = (a->w + 15) / 16, tiles_y = (a->h + 7) / 8;
+    dim3 grid(tiles_x * tiles_y, (a->c + 31) / 32, a->batch);
+    RB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "dwconv: grid too large");
+    if (a->dtype == RB_F32) dwconv5x5_relu_kernel<float><<<grid, 256, 0, st>>>((const float*)a->in, (float*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
+    else if (a->dtype == RB_F16) dwconv5x5_relu_kernel<__half><<<grid, 256, 0, st>>>((const __half*)a->in, (__half*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
+    else dwconv5x5_relu_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
+    return check_launch("dwconv5x5_relu");
+}
+
+extern "C" int romab200_refiner_tail(const rb_refiner_tail_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned grid = (unsigned)((a->rows + 7) / 8);
+    if (a->dtype == RB_F32) refiner_tail_kernel<float><<<grid, 256, 0, st>>>((const float*)a->d, a->ldd, a->weight, a->ldw, a->bias, a->state, a->rows, a->c, a->scale_x, a->scale_y, a->delta_out);
+    else if (a->dtype == RB_F16) refiner_tail_kernel<__half><<<grid, 256, 0, st>>>((const __half*)a->d, a->ldd, a->weight, a->ldw, a->bias, a->state, a->rows, a->c, a->scale_x, a->scale_y, a->delta_out);
+    else refiner_tail_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->d, a->ldd, a->weight, a->ldw, a->bias, a->state, a->rows, a->c, a->scale_x, a->scale_y, a->delta_out);
+    return check_launch("refiner_tail");
+}
+
+extern "C" int romab200_bilinear_resize(const rb_resize_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t total = (int64_t)a->batch * a->ho * a->wo * a->c;
+    RB_REQUIRE(total > 0, "bilinear_resize: empty");
+    bilinear_resize_kernel<<<grid1d(total, 256), 256, 0, st>>>(a->in, a->out, a->batch, a->hi, a->wi, a->ho, a->wo, a->c);
+    return check_launch("bilinear_resize");
+}
+
+extern "C" int romab200_cls_to_flow_refine(const rb_cls_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->rows > 0 && a->rows < (1ll << 31) && a->ldl > (int64_t)a->res * a->res, "cls_to_flow_refine: bad shape");
+    if (a->dtype == RB_F32) cls_to_flow_kernel<float><<<(unsigned)a->rows, 256, 0, st>>>((const float*)a->logits, a->state, a->ldl, a->res);
+    else if (a->dtype == RB_F16) cls_to_flow_kernel<__half><<<(unsigned)a->rows, 256, 0, st>>>((const __half*)a->logits, a->state, a->ldl, a->res);
+    else cls_to_flow_kernel<__nv_bfloat16><<<(unsigned)a->rows, 256, 0, st>>>((const __nv_bfloat16*)a->logits, a->state, a->ldl, a->res);
+    return check_launch("cls_to_flow_refine");
+}
+
+extern "C" int romab200_match_epilogue(const rb_match_epilogue_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int D = a->symmetric ? 2 * a->b : a->b;
+    int64_t total = (int64_t)D * a->H * a->W;
+    RB_REQUIRE(total > 0 && a->grid_x && a->grid_y, "match_epilogue: bad arguments");
+    match_epilogue_kernel<<<grid1d(total, 256), 256, 0, st>>>(a->state, a->coarse_state, a->hc, a->wc, a->warp, a->cert, a->b, a->H, a->W,
+                                                              a->symmetric, a->grid_x, a->grid_y);
+    return check_launch("match_epilogue");
+}

@@ -1,0 +1,92 @@
+// VGG19-BN pieces that are not GEMMs (romatch/models/encoders.py:17-27):
+//   * the first 3->64 convolution (K = 27 is too thin for a GEMM tile): direct conv from the NCHW fp32
+//     image into the zero-padded channels-last layout every later 3x3 layer uses;
+//   * 2x2 max-pool between zero-padded channels-last maps.
+// Both are HBM-bound streaming kernels.
+#include "common.cuh"
+
+namespace rb {
+
+// one thread per output pixel, 64 output channels in 4 groups of 16 accumulators; weights in shared memory
+// (every lane reads the same address -> broadcast).  Inputs are read coalesced along x from the 3 planes.
+template <typename TO>
+__global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restrict__ img, TO* __restrict__ out,
+                                                            const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                            int B, int H, int W, int COUT) {
+    extern __shared__ float sw[];   // [COUT][27] + [COUT]
+    for (int i = threadIdx.x; i < COUT * 27; i += blockDim.x) sw[i] = wgt[i];
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) sw[COUT * 27 + i] = bias[i];
+    __syncthreads();
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    float in[27];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                int yy = y + ky - 1, xx = x + kx - 1;
+                float v = 0.f;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = img[(((int64_t)b * 3 + c) * H + yy) * W + xx];
+                in[c * 9 + ky * 3 + kx] = v;
+            }
+    TO* o = out + (((int64_t)b * (H + 2) + (y + 1)) * (W + 2) + (x + 1)) * COUT;
+    for (int g = 0; g < COUT; g += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = sw[COUT * 27 + g + j];
+            const float* wj = sw + (g + j) * 27;
+#pragma unroll
+            for (int t = 0; t < 27; ++t) a = fmaf(in[t], wj[t], a);
+            acc[j] = fmaxf(a, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[g + j] = from_f<TO>(acc[j]);
+    }
+}
+
+// thread per (output pixel, channel); channels fastest -> coalesced
+template <typename T>
+__global__ void maxpool2x2_padded_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C) {
+    int Ho = H / 2, Wo = W / 2;
+    int64_t total = (int64_t)B * Ho * Wo * C;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(idx % C); int64_t p = idx / C;
+        int xo = (int)(p % Wo); int yo = (int)((p / Wo) % Ho); int b = (int)(p / ((int64_t)Wo * Ho));
+        const T* s = in + (((int64_t)b * (H + 2) + (2 * yo + 1)) * (W + 2) + (2 * xo + 1)) * C + c;
+        int64_t rs = (int64_t)(W + 2) * C;
+        float v = fmaxf(fmaxf(to_f(s[0]), to_f(s[C])), fmaxf(to_f(s[rs]), to_f(s[rs + C])));
+        out[(((int64_t)b * (Ho + 2) + (yo + 1)) * (Wo + 2) + (xo + 1)) * C + c] = from_f<T>(v);
+    }
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" int romab200_conv3x3_first(const rb_conv_first_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->cout % 8 == 0 && a->cout <= 256, "conv3x3_first: cout=%d", a->cout);
+    RB_REQUIRE(a->height <= 65535 && a->batch <= 65535, "conv3x3_first: grid too large");
+    dim3 grid((a->width + 127) / 128, a->height, a->batch);
+    size_t smem = (size_t)a->cout * 28 * sizeof(float);
+    if (a->dtype_out == RB_F32) conv3x3_first_kernel<float><<<grid, 128, smem, st>>>(a->image, (float*)a->out, a->weight, a->bias, a->batch, a->height, a->width, a->cout);
+    else if (a->dtype_out == RB_F16) conv3x3_first_kernel<__half><<<grid, 128, smem, st>>>(a->image, (__half*)a->out, a->weight, a->bias, a->batch, a->height, a->width, a->cout);
+    else conv3x3_first_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>(a->image, (__nv_bfloat16*)a->out, a->weight, a->bias, a->batch, a->height, a->width, a->cout);
+    return check_launch("conv3x3_first");
+}
+
+extern "C" int romab200_maxpool2x2_padded(const rb_maxpool_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t total = (int64_t)a->batch * (a->height / 2) * (a->width / 2) * a->channels;
+    RB_REQUIRE(total > 0, "maxpool: empty");
+    int64_t g = (total + 255) / 256; if (g > 148 * 64) g = 148 * 64;
+    if (a->dtype == RB_F32) maxpool2x2_padded_kernel<float><<<(unsigned)g, 256, 0, st>>>((const float*)a->in, (float*)a->out, a->batch, a->height, a->width, a->channels);
+    else if (a->dtype == RB_F16) maxpool2x2_padded_kernel<__half><<<(unsigned)g, 256, 0, st>>>((const __half*)a->in, (__half*)a->out, a->batch, a->height, a->width, a->channels);
+    else maxpool2x2_padded_kernel<__nv_bfloat16><<<(unsigned)g, 256, 0, st>>>((const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->batch, a->height, a->width, a->channels);
+    return check_launch("maxpool2x2_padded");
+}

@@ -1,0 +1,379 @@
+"""Device pipeline of RoMa's dense matcher: orchestrates the libromab200 kernels.
+
+One `Engine` owns the packed weights, the per-resolution constants and a cache of activation buffers,
+and enqueues the whole of `forward_symmetric` / `forward` (`romatch/models/matcher.py:631-670`) plus the
+`match()` epilogue on the current CUDA stream through the C ABI.  PyTorch is used for device memory
+(`torch.empty/zeros`) and streams only; every arithmetic step is one of our kernels.
+
+Precision regimes (`precision=`):
+  "fp32"        parity mode: fp32 operands and CUDA-core FFMA GEMMs everywhere, comparable to the
+                reference's CPU fp32 path at the 1e-4 level (tests/test_e2e_parity.py);
+  "fp16"/"bf16" fast mode, mirrors the reference's CUDA autocast regime (`utils.py:639-653`): 16-bit GEMM
+                operands on the tcgen05 tensor pipe with fp32 accumulation, fp32 residual stream,
+                LayerNorm, softmax statistics, GP solve, local-correlation accumulation, heads and
+                flow/certainty state.
+
+Data layout: channels-last everywhere.  VGG maps carry a 1-pixel zero border ([E, H+2, W+2, C]) so that a
+3x3 convolution is a 9-tap shifted-row GEMM over the flattened padded grid.  Flow and certainty travel
+together as a 3-channel fp32 state map [D, h, w, 3].
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import arch, cabi
+from .cabi import call
+from .packing import PackedWeights, pad8
+
+PRECISIONS = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+class Engine:
+    def __init__(self, matcher_sd, dino_sd, device, precision: str = "fp32"):
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {list(PRECISIONS)}")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("roma_b200 runs on a CUDA device only (there is no CPU fallback); "
+                               f"got device={device!r}")
+        cabi.load_library()
+        self.precision = precision
+        self.dtype = PRECISIONS[precision]
+        self.dt = cabi.DTYPE_CODE[self.dtype]
+        with torch.cuda.device(self.device):
+            self.w = PackedWeights(matcher_sd, dino_sd, self.device, self.dtype)
+        self._buf: Dict[tuple, torch.Tensor] = {}
+        self._const: Dict[tuple, torch.Tensor] = {}
+        self.debug: Optional[dict] = None        # set to {} to keep stage tensors (tests)
+
+    # ------------------------------------------------------------------ buffers and constants
+    def buf(self, name, shape, dtype=None, zero=False):
+        dtype = dtype or self.dtype
+        key = (name, tuple(shape), dtype)
+        t = self._buf.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
+            self._buf[key] = t
+        return t
+
+    def free_buffers(self):
+        self._buf.clear()
+
+    def const(self, key, make):
+        t = self._const.get(key)
+        if t is None:
+            t = make().to(self.device)
+            self._const[key] = t
+        return t
+
+    def grid_axis(self, n):
+        """linspace(-1+1/n, 1-1/n, n): pixel-centre coordinates (matcher.py:365-377)."""
+        return self.const(("grid", n), lambda: torch.linspace(-1 + 1 / n, 1 - 1 / n, n))
+
+    def window_axis(self, r, n):
+        """linspace(-2r/n, 2r/n, 2r+1): local-correlation window offsets (local_correlation.py:93-103)."""
+        return self.const(("win", r, n), lambda: torch.linspace(-2 * r / n, 2 * r / n, 2 * r + 1))
+
+    def pos_embed(self, hp, wp):
+        """DINOv2 positional embedding resized exactly as `interpolate_pos_encoding` does (dinov2.py:166-190):
+        bicubic with scale_factor=(hp+0.1)/37 (NOT size=), computed once per resolution on the host."""
+        def make():
+            pe = self.w.vit_pos_embed
+            n = pe.shape[1] - 1
+            side = int(math.sqrt(n))
+            if hp * wp == n and hp == wp:
+                return pe[0].clone()
+            grid = pe[:, 1:].reshape(1, side, side, -1).permute(0, 3, 1, 2)
+            grid = F.interpolate(grid, scale_factor=((hp + 0.1) / side, (wp + 0.1) / side), mode="bicubic")
+            assert grid.shape[-2:] == (hp, wp)
+            return torch.cat((pe[0, :1], grid.permute(0, 2, 3, 1).reshape(hp * wp, -1)), dim=0).contiguous()
+        return self.const(("pos", hp, wp), make)
+
+    def gp_basis_t(self, h, w):
+        """F^T [512, h*w]: cos(8*pi*pos_conv(pixel-centre grid)) (matcher.py:264-289), a per-resolution constant."""
+        def make():
+            ys = torch.linspace(-1 + 1 / h, 1 - 1 / h, h)
+            xs = torch.linspace(-1 + 1 / w, 1 - 1 / w, w)
+            gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+            coords = torch.stack((gx, gy))[None]
+            f = torch.cos(8 * math.pi * F.conv2d(coords, self.w.gp_pos_w, self.w.gp_pos_b))
+            return f[0].reshape(arch.GP_DIM, h * w).contiguous()
+        return self.const(("gpbasis", h, w), make)
+
+    # ------------------------------------------------------------------ kernel wrappers
+    def gemm(self, A, B, C, M, N, K, lda, ldb, ldc, dtype_ab=None, dtype_c=None, **kw):
+        args = dict(A=A, B=B, C=C, M=M, N=N, K=K, lda=lda, ldb=ldb, ldc=ldc,
+                    dtype_ab=self.dt if dtype_ab is None else dtype_ab,
+                    dtype_c=self.dt if dtype_c is None else dtype_c,
+                    batch0=1, batch1=1, ntaps=1, alpha=1.0)
+        args.update(kw)
+        call("romab200_gemm", "rb_gemm_args", **args)
+
+    def layernorm(self, x, y, gb, rows, cols, eps, dtype_y=None):
+        call("romab200_layernorm", "rb_layernorm_args", x=x, y=y, gamma=gb[0], beta=gb[1], rows=rows, cols=cols,
+             ldx=cols, ldy=cols, dtype_x=cabi.RB_F32, dtype_y=self.dt if dtype_y is None else dtype_y, eps=eps)
+
+    def copy2d(self, src, dst, rows, cols, lds, ldd, ds, dd):
+        call("romab200_copy2d", "rb_copy2d_args", src=src, dst=dst, rows=rows, cols=cols, lds=lds, ldd=ldd,
+             dtype_src=ds, dtype_dst=dd)
+
+    # ------------------------------------------------------------------ VGG19-BN (encoders.py:17-27)
+    def vgg(self, image: torch.Tensor, tag: str):
+        """image [E,3,H,W] fp32 -> {s: zero-padded channels-last tap [E, H/s+2, W/s+2, C_s]} for s in 1,2,4,8."""
+        E, _, H, W = image.shape
+        taps = {}
+        layers = self.w.vgg
+        h, w = H, W
+        cur = self.buf(f"vgg{tag}.s1.in", (E, h + 2, w + 2, 64), zero=True)
+        call("romab200_conv3x3_first", "rb_conv_first_args", image=image, out=cur, weight=layers[0]["w"], bias=layers[0]["b"],
+             batch=E, height=h, width=w, cout=64, dtype_out=self.dt)
+        li, scale = 1, 1
+        for nconv in (1, 2, 4, 4):                              # convs left in each stage after conv0
+            for j in range(nconv):
+                L = layers[li]
+                li += 1
+                nxt = self.buf(f"vgg{tag}.s{scale}.p{j % 2}", (E, h + 2, w + 2, L["cout"]), zero=True)
+                rows = E * (h + 2) * (w + 2)
+                taps_rows = [(ky - 1) * (w + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
+                self.gemm(cur, L["w"], nxt, rows, L["cout"], 9 * L["cin"], L["cin"], 9 * L["cin"], L["cout"],
+                          ntaps=9, tap_rows=taps_rows, a_rows=rows, bias=L["b"], act=cabi.ACT_RELU,
+                          rowmap=cabi.ROWMAP_PAD_KEEP, pad_h=h + 2, pad_w=w + 2)
+                cur = nxt
+            taps[scale] = (cur, h, w)
+            if scale == 8:
+                break
+            c = layers[li - 1]["cout"]
+            pooled = self.buf(f"vgg{tag}.s{scale * 2}.in", (E, h // 2 + 2, w // 2 + 2, c), zero=True)
+            call("romab200_maxpool2x2_padded", "rb_maxpool_args", **{"in": cur}, out=pooled, batch=E, height=h, width=w,
+                 channels=c, dtype=self.dt)
+            cur, h, w, scale = pooled, h // 2, w // 2, scale * 2
+        return taps
+
+    # ------------------------------------------------------------------ transformer blocks
+    def attention(self, qkv, out, Bn, N, heads, dim, tag):
+        """softmax(q k^T / sqrt(d)) v per head (F.scaled_dot_product_attention, attention.py:50-63).
+        qkv [Bn, N, 3*dim] (q|k|v, heads contiguous inside each) -> out [Bn, N, dim]."""
+        d = dim // heads
+        npad = pad8(N)
+        sdt = self.dtype
+        S = self.buf(f"attn.scores.{tag}", (Bn, heads, N, npad), dtype=sdt)
+        ld = 3 * dim
+        es = qkv.element_size()
+        q_ptr, k_ptr, v_ptr = qkv.data_ptr(), qkv.data_ptr() + dim * es, qkv.data_ptr() + 2 * dim * es
+        self.gemm(q_ptr, k_ptr, S, N, N, d, ld, ld, npad, batch0=Bn, batch1=heads,
+                  sa0=N * ld, sa1=d, sb0=N * ld, sb1=d, sc0=heads * N * npad, sc1=N * npad)
+        call("romab200_softmax_rows", "rb_softmax_args", s=S, rows=Bn * heads * N, cols=N, lds=npad, dtype=self.dt,
+             scale=1.0 / math.sqrt(d))
+        self.gemm(S, v_ptr, out, N, d, N, npad, ld, dim, trans_b=1, batch0=Bn, batch1=heads,
+                  sa0=heads * N * npad, sa1=N * npad, sb0=N * ld, sb1=d, sc0=N * dim, sc1=d)
+
+    def block(self, x, blk, Bn, N, dim, heads, mlp, eps, tag):
+        """pre-LN transformer block on the fp32 residual stream x [Bn*N, dim] (block.py:82-107)."""
+        rows = Bn * N
+        xn = self.buf(f"blk.xn.{tag}", (rows, dim))
+        qkv = self.buf(f"blk.qkv.{tag}", (rows, 3 * dim))
+        att = self.buf(f"blk.att.{tag}", (rows, dim))
+        hid = self.buf(f"blk.hid.{tag}", (rows, mlp))
+        self.layernorm(x, xn, blk["ln1"], rows, dim, eps)
+        self.gemm(xn, blk["qkv_w"], qkv, rows, 3 * dim, dim, dim, dim, 3 * dim, bias=blk["qkv_b"])
+        self.attention(qkv, att, Bn, N, heads, dim, tag)
+        self.gemm(att, blk["proj_w"], x, rows, dim, dim, dim, dim, dim, dtype_c=cabi.RB_F32, bias=blk["proj_b"],
+                  col_scale=blk["ls1"], R=x, ldr=dim, dtype_r=cabi.RB_F32)
+        self.layernorm(x, xn, blk["ln2"], rows, dim, eps)
+        self.gemm(xn, blk["fc1_w"], hid, rows, mlp, dim, dim, dim, mlp, bias=blk["fc1_b"], act=cabi.ACT_GELU)
+        self.gemm(hid, blk["fc2_w"], x, rows, dim, mlp, mlp, mlp, dim, dtype_c=cabi.RB_F32, bias=blk["fc2_b"],
+                  col_scale=blk["ls2"], R=x, ldr=dim, dtype_r=cabi.RB_F32)
+
+    # ------------------------------------------------------------------ DINOv2 ViT-L/14 (encoders.py:60-67)
+    def dinov2(self, image: torch.Tensor):
+        """image [E,3,H,W] fp32 -> patch tokens [E, hp*wp, 1024] in the compute dtype (channels-last stride-14 map)."""
+        E, _, H, W = image.shape
+        hp, wp = H // arch.VIT_PATCH, W // arch.VIT_PATCH
+        npatch, dim = hp * wp, arch.VIT_DIM
+        N = npatch + 1
+        kp = self.w.vit_patch_w.shape[1]
+        cols = self.buf("vit.im2col", (E * npatch, kp), zero=True)
+        call("romab200_im2col_patch", "rb_im2col_args", image=image, out=cols, batch=E, height=H, width=W,
+             patch=arch.VIT_PATCH, ldo=kp, dtype_out=self.dt)
+        patch = self.buf("vit.patch", (E * npatch, dim), dtype=torch.float32)
+        self.gemm(cols, self.w.vit_patch_w, patch, E * npatch, dim, 3 * arch.VIT_PATCH ** 2, kp, kp, dim,
+                  dtype_c=cabi.RB_F32, bias=self.w.vit_patch_b)
+        x = self.buf("vit.x", (E * N, dim), dtype=torch.float32)
+        call("romab200_assemble_tokens", "rb_tokens_args", patch=patch, cls=self.w.vit_cls, pos=self.pos_embed(hp, wp),
+             tokens=x, batch=E, npatch=npatch, dim=dim)
+        for blk in self.w.vit:
+            self.block(x, blk, E, N, dim, arch.VIT_HEADS, arch.VIT_MLP, arch.VIT_LN_EPS, "vit")
+        out = self.buf("vit.out", (E * N, dim))
+        self.layernorm(x, out, self.w.vit_norm, E * N, dim, arch.VIT_LN_EPS)
+        feats = self.buf("vit.feat16", (E, npatch, dim))
+        # drop the cls token: rows 1..N of every image
+        for e in range(E):
+            self.copy2d(out.data_ptr() + (e * N + 1) * dim * out.element_size(), feats.data_ptr() + e * npatch * dim * feats.element_size(),
+                        npatch, dim, dim, dim, self.dt, self.dt)
+        return feats, hp, wp
+
+    # ------------------------------------------------------------------ proj (roma_models.py:156-169)
+    def proj_from_padded(self, s, tap, E, h, w, tag):
+        """1x1 conv + folded BN on a zero-padded tap -> compact channels-last [E, h, w, cout]."""
+        cin, cout = arch.PROJ[s]
+        P = self.w.proj[s]
+        out = self.buf(f"proj{tag}.{s}", (E, h, w, pad8(cout)), zero=True)
+        rows = E * (h + 2) * (w + 2)
+        self.gemm(tap, P["w"], out, rows, cout, cin, cin, P["w"].shape[1], pad8(cout), bias=P["b"],
+                  rowmap=cabi.ROWMAP_PAD_TO_COMPACT, pad_h=h + 2, pad_w=w + 2)
+        return out
+
+    # ------------------------------------------------------------------ GP + transformer decoder (scale 16)
+    def coarse_match(self, feat16, E, D, b, hp, wp, state):
+        """GP posterior (matcher.py:291-323), embedding decoder (transformer/__init__.py:30-46) and
+        cls_to_flow_refine (utils.py:300-322): fills state [D, hp, wp, 3]; returns the projected features."""
+        n = hp * wp
+        cin, cf = arch.PROJ[16]
+        P = self.w.proj[16]
+        f32 = cabi.RB_F32
+        p16 = self.buf("gp.p16", (E * n, cf), dtype=torch.float32)      # GP runs in fp32 (x.float(), matcher.py:296)
+        self.gemm(feat16, P["w"], p16, E * n, cf, cin, cin, P["w"].shape[1], cf, dtype_c=f32, bias=P["b"])
+        norms = self.buf("gp.norms", (E * n,), dtype=torch.float32)
+        call("romab200_row_norms", "rb_rownorm_args", x=p16, out=norms, rows=E * n, cols=cf, ldx=cf, dtype=f32)
+        ldw = pad8(n)
+        nrhs = arch.GP_DIM
+        Wk = self.buf("gp.work", (E, n + nrhs, ldw), dtype=torch.float32)
+        stride_w = (n + nrhs) * ldw
+        # K_yy + sigma*I for every image (its own features): exp((cos-1)/T)   (matcher.py:191-200, 298, 301)
+        self.gp_kernel_matrix(p16, p16, norms, norms, Wk, n, cf, ldw, batch=E, sa=n * cf, sb=n * cf, sc=stride_w,
+                              sna=n, snb=n, diag=arch.GP_SIGMA_NOISE)
+        basis_t = self.gp_basis_t(hp, wp)
+        for e in range(E):
+            self.copy2d(basis_t, Wk.data_ptr() + (e * stride_w + n * ldw) * 4, nrhs, n, n, ldw, f32, f32)
+        call("romab200_gp_solve", "rb_gp_solve_args", W=Wk, n=n, nrhs=nrhs, batch=E, ldw=ldw, stride=stride_w)
+        # K_xy and mu = K_xy @ alpha for every decoder item: query image i, support image (i + b) % E
+        kxy = self.buf("gp.kxy", (D, n, ldw), dtype=torch.float32)
+        dim = arch.DEC_DIM
+        tokens = self.buf("dec.tokens_in", (D * n, dim))
+        es = tokens.element_size()
+        halves = [(0, b, b)] if D == b else [(0, b, b), (b, b, 0)]     # (first item, count, first support image)
+        for i0, cnt, y0 in halves:
+            self.gp_kernel_matrix(p16.data_ptr() + i0 * n * cf * 4, p16.data_ptr() + y0 * n * cf * 4,
+                                  norms.data_ptr() + i0 * n * 4, norms.data_ptr() + y0 * n * 4,
+                                  kxy.data_ptr() + i0 * n * ldw * 4, n, cf, ldw, batch=cnt, sa=n * cf, sb=n * cf, sc=n * ldw,
+                                  sna=n, snb=n, diag=0.0)
+            self.gemm(kxy.data_ptr() + i0 * n * ldw * 4, Wk.data_ptr() + (y0 * stride_w + n * ldw) * 4,
+                      tokens.data_ptr() + i0 * n * dim * es, n, nrhs, n, ldw, ldw, dim, dtype_ab=f32,
+                      batch0=cnt, sa0=n * ldw, sb0=stride_w, sc0=n * dim)
+        # tokens = cat(gp_posterior, f1_s) (transformer/__init__.py:33)
+        self.copy2d(p16, tokens.data_ptr() + arch.GP_DIM * es, D * n, cf, cf, dim, f32, self.dt)
+        if self.debug is not None:
+            self.debug["gp.mu"] = tokens.view(D, n, dim)[:, :, :arch.GP_DIM].float().clone()
+        x = self.buf("dec.x", (D * n, dim), dtype=torch.float32)
+        self.copy2d(tokens, x, D * n, dim, dim, dim, self.dt, f32)
+        for blk in self.w.dec:
+            self.block(x, blk, D, n, dim, arch.DEC_HEADS, arch.DEC_MLP, arch.DEC_LN_EPS, "dec")
+        xa = self.buf("dec.xa", (D * n, dim))
+        self.copy2d(x, xa, D * n, dim, dim, dim, f32, self.dt)
+        ldl = pad8(arch.CLS_OUT)
+        logits = self.buf("dec.logits", (D * n, ldl), dtype=torch.float32)
+        self.gemm(xa, self.w.to_out_w, logits, D * n, arch.CLS_OUT, dim, dim, dim, ldl, dtype_c=f32, bias=self.w.to_out_b)
+        call("romab200_cls_to_flow_refine", "rb_cls_args", logits=logits, state=state, rows=D * n, ldl=ldl,
+             res=arch.CLS_RES, dtype=f32)
+        if self.debug is not None:
+            self.debug["cls"] = logits.view(D, n, ldl)[:, :, :arch.CLS_OUT].clone()
+        # the stride-16 refiner consumes the same projected features (matcher.py:450,484-486)
+        feat = self.buf("proj.16", (E, hp, wp, cf))
+        self.copy2d(p16, feat, E * n, cf, cf, cf, f32, self.dt)
+        return feat
+
+    def gp_kernel_matrix(self, A, B, na, nb, C, n, cf, ldc, batch, sa, sb, sc, sna, snb, diag):
+        """C[z] = exp((cos(A[z], B[z]) - 1) / T) + diag*I  — the all-pairs CosKernel contraction."""
+        self.gemm(A, B, C, n, n, cf, cf, cf, ldc, dtype_ab=cabi.RB_F32, dtype_c=cabi.RB_F32, batch0=batch,
+                  sa0=sa, sb0=sb, sc0=sc, epi=cabi.EPI_COSKERNEL, norm_a=na, norm_b=nb, sna0=sna, snb0=snb,
+                  eps=arch.GP_COS_EPS, inv_t=1.0 / arch.GP_TEMPERATURE, diag_add=diag, cos_normalized=0)
+
+    # ------------------------------------------------------------------ ConvRefiner (matcher.py:124-179)
+    def refine(self, s, feat, ldf, E, D, b, h, w, state, scale_factor, h1, w1, tag):
+        R = self.w.refiner[s]
+        spec, c, cp = R["spec"], R["c"], R["cp"]
+        d = self.buf(f"ref.d.{tag}", (D * h * w, cp), zero=True)
+        t = self.buf(f"ref.t.{tag}", (D * h * w, cp), zero=True)
+        r = spec.radius
+        call("romab200_refiner_prologue", "rb_refiner_prologue_args", feat=feat, ldf=ldf, n_img=E, y_shift=b,
+             state=state, d=d, ldd=cp, D=D, h=h, w=w, cf=spec.feat, emb=spec.emb, radius=r, dtype=self.dt,
+             emb_weight=R["emb_w"], emb_bias=R["emb_b"],
+             disp_scale=float(torch.tensor(40 / 32 * scale_factor, dtype=torch.float32)),
+             grid_x=self.grid_axis(w), grid_y=self.grid_axis(h),
+             win_x=self.window_axis(r, w) if r else None, win_y=self.window_axis(r, h) if r else None)
+        if self.debug is not None:
+            self.debug[f"{tag}.refiner_in"] = d.view(D, h, w, cp)[..., :c].float().clone()
+        rows = D * h * w
+        for blk in R["blocks"]:
+            call("romab200_dwconv5x5_relu", "rb_dwconv_args", **{"in": d}, out=t, ldi=cp, ldo=cp, weight=blk["dw_w"], ldw=cp,
+                 bias=blk["dw_b"], batch=D, h=h, w=w, c=c, dtype=self.dt)
+            self.gemm(t, blk["pw_w"], d, rows, c, c, cp, cp, cp, bias=blk["pw_b"])
+        delta = self.buf(f"ref.delta.{tag}", (rows, 3), dtype=torch.float32) if self.debug is not None else None
+        call("romab200_refiner_tail", "rb_refiner_tail_args", d=d, ldd=cp, weight=R["out_w"], ldw=cp, bias=R["out_b"],
+             state=state, rows=rows, c=c, scale_x=s / (arch.REFINE_INIT * w1), scale_y=s / (arch.REFINE_INIT * h1),
+             dtype=self.dt, delta_out=delta)
+        if self.debug is not None:
+            self.debug[f"{tag}.delta"] = delta.view(D, h, w, 3).clone()
+
+    def resize_state(self, src, D, hi, wi, ho, wo, name):
+        dst = self.buf(name, (D, ho, wo, 3), dtype=torch.float32)
+        call("romab200_bilinear_resize", "rb_resize_args", **{"in": src}, out=dst, batch=D, hi=hi, wi=wi, ho=ho, wo=wo, c=3)
+        return dst
+
+    # ------------------------------------------------------------------ one pass of the matcher
+    def run_pass(self, images: torch.Tensor, b: int, symmetric: bool, upsample: bool, scale_factor: float,
+                 state_in: Optional[Tuple[torch.Tensor, int, int]] = None, keep_states=False):
+        """images [2b,3,H,W] fp32 (A batch then B batch).  Returns (state [D,H,W,3], states per scale)."""
+        tag = "up" if upsample else "lo"
+        E = 2 * b
+        D = E if symmetric else b
+        _, _, H, W = images.shape
+        taps = self.vgg(images, tag)
+        sizes = {s: (taps[s][1], taps[s][2]) for s in (1, 2, 4, 8)}
+        states = {}
+        if not upsample:
+            feat16_raw, hp, wp = self.dinov2(images)
+            sizes[16] = (hp, wp)
+            state = self.buf("state.lo.16", (D, hp, wp, 3), dtype=torch.float32)
+            feat16 = self.coarse_match(feat16_raw, E, D, b, hp, wp, state)
+            if self.debug is not None:
+                self.debug["coarse_state"] = state.clone()
+            scales = arch.SCALES
+        else:
+            src, hi, wi = state_in
+            state = self.resize_state(src, D, hi, wi, *sizes[8], name="state.up.8")
+            scales = arch.UPSAMPLE_SCALES
+        for s in scales:
+            h, w = sizes[s]
+            if s == 16:
+                feat, ldf = feat16, arch.PROJ[16][1]
+            else:
+                feat = self.proj_from_padded(s, taps[s][0], E, h, w, tag)
+                ldf = pad8(arch.PROJ[s][1])
+            if self.debug is not None:
+                self.debug[f"{tag}.proj{s}"] = feat.view(E, h, w, -1)[..., :arch.PROJ[s][1]].float().clone()
+            self.refine(s, feat, ldf, E, D, b, h, w, state, scale_factor, H, W, f"{tag}{s}")
+            if keep_states or s == 16:
+                states[s] = state.clone() if keep_states else state
+            if s != 1:
+                ho, wo = sizes[s // 2]
+                state = self.resize_state(state, D, h, w, ho, wo, name=f"state.{tag}.{s // 2}")
+        return state, states, sizes
+
+    def epilogue(self, state, coarse_state, hc, wc, b, H, W, symmetric):
+        Wout = 2 * W if symmetric else W
+        warp = torch.empty(b, H, Wout, 4, dtype=torch.float32, device=self.device)
+        cert = torch.empty(b, H, Wout, dtype=torch.float32, device=self.device)
+        call("romab200_match_epilogue", "rb_match_epilogue_args", state=state, coarse_state=coarse_state, hc=hc, wc=wc,
+             warp=warp, cert=cert, b=b, H=H, W=W, symmetric=int(symmetric), grid_x=self.grid_axis(W), grid_y=self.grid_axis(H))
+        return warp, cert
+
+    def kde(self, x: torch.Tensor, std: float = 0.1, half: bool = True):
+        x = x.contiguous().float()
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        call("romab200_kde_density", "rb_kde_args", x=x, density=out, n=x.shape[0], std=std, half=int(half))
+        return out

@@ -1,0 +1,252 @@
+"""`RegressionMatcher`: the reference's public matcher API on top of the B200 engine.
+
+Mirrors `romatch.models.matcher.RegressionMatcher` (`romatch/models/matcher.py:550-986`): same
+constructor-level attributes (mutable, as the reference's README documents), same method names,
+argument meaning, return shapes/dtypes and error behaviour, so that callers (`demo/*.py`,
+`romatch/benchmarks/*`) can switch implementation without edits.  The heavy lifting (`match`, `forward`,
+the KDE inside `sample`) runs in the hand-written CUDA kernels behind `roma_b200.engine.Engine`; the small
+geometry helpers are plain tensor arithmetic on whatever device their inputs live on.
+"""
+from __future__ import annotations
+
+import math
+import os
+from warnings import warn
+
+import torch
+import torch.nn.functional as F
+from PIL import Image
+
+from .engine import Engine
+from .preprocess import check_input, pil_to_normalized
+
+
+class RegressionMatcher:
+    def __init__(self, engine: Engine, h=448, w=448, sample_mode="threshold_balanced", upsample_preds=False,
+                 symmetric=False, sample_thresh=0.05, name=None, attenuate_cert=None, upsample_res=None):
+        self.engine = engine
+        self.attenuate_cert = attenuate_cert
+        self.name = name
+        self.w_resized = w
+        self.h_resized = h
+        self.sample_mode = sample_mode
+        self.upsample_preds = upsample_preds
+        self.upsample_res = upsample_res or (14 * 16 * 6, 14 * 16 * 6)      # matcher.py:575
+        self.symmetric = symmetric
+        self.sample_thresh = sample_thresh
+        self.training = False
+
+    # ---- nn.Module-ish conveniences callers rely on ------------------------------------------------
+    def train(self, mode: bool = True):
+        self.training = False      # inference-only implementation; match() forces eval (matcher.py:790)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def to(self, *args, **kwargs):
+        return self
+
+    def _get_device(self):
+        return self.engine.device
+
+    def get_output_resolution(self):
+        if not self.upsample_preds:
+            return self.h_resized, self.w_resized
+        return self.upsample_res
+
+    # ---- dense matching -----------------------------------------------------------------------------
+    def _states_to_corresps(self, states):
+        return {s: {"flow": st[..., :2].permute(0, 3, 1, 2), "certainty": st[..., 2:3].permute(0, 3, 1, 2)}
+                for s, st in states.items()}
+
+    @torch.inference_mode()
+    def forward(self, batch, batched=True, upsample=False, scale_factor=1):
+        """{scale: {"flow" [B,2,h,w], "certainty" [B,1,h,w]}} like `RegressionMatcher.forward` (matcher.py:631-652)."""
+        return self._forward(batch, False, upsample, scale_factor)
+
+    @torch.inference_mode()
+    def forward_symmetric(self, batch, batched=True, upsample=False, scale_factor=1):
+        return self._forward(batch, True, upsample, scale_factor)
+
+    def _forward(self, batch, symmetric, upsample, scale_factor):
+        eng = self.engine
+        im_a = batch["im_A"].to(eng.device, torch.float32)
+        im_b = batch["im_B"].to(eng.device, torch.float32)
+        images = torch.cat((im_a, im_b)).contiguous()
+        state_in = None
+        if upsample:
+            c = batch["corresps"]
+            st = torch.cat((c["flow"], c["certainty"]), dim=1).permute(0, 2, 3, 1).contiguous().float()
+            state_in = (st, st.shape[1], st.shape[2])
+        with torch.cuda.device(eng.device):
+            _, states, _ = eng.run_pass(images, im_a.shape[0], symmetric, upsample, float(scale_factor), state_in,
+                                        keep_states=True)
+        return self._states_to_corresps(states)
+
+    @torch.inference_mode()
+    def match(self, im_A_input, im_B_input, *args, im_A_high_res=None, im_B_high_res=None, batched=True, device=None):
+        """Dense warp and certainty (matcher.py:779-934).  Returns (warp [b,H,W*(2 if symmetric),4] fp32 in
+        [-1,1], certainty [b,H,W*(2)] fp32 in [0,1]); extra positional args are ignored like the reference."""
+        if not batched:
+            raise ValueError("batched must be True, non-batched inference is no longer supported.")
+        eng = self.engine
+        if device is None:
+            device = eng.device
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("roma_b200 computes on CUDA only; device=%r" % (device,))
+        im_A = check_input(im_A_input)
+        im_B = check_input(im_B_input)
+        symmetric = self.symmetric
+        ws, hs = self.w_resized, self.h_resized
+        scale_factor = math.sqrt(hs * ws / (560 ** 2))
+        pil_route = isinstance(im_A, Image.Image) and isinstance(im_B, Image.Image)
+        if pil_route:
+            b = 1
+            a_t = pil_to_normalized(im_A, (hs, ws))[None]
+            b_t = pil_to_normalized(im_B, (hs, ws))[None]
+        elif isinstance(im_A, torch.Tensor) and isinstance(im_B, torch.Tensor):
+            b, c, h, w = im_A.shape
+            b, c, h2, w2 = im_B.shape
+            assert w == w2 and h == h2, "For batched images we assume same size"
+            if h != self.h_resized or self.w_resized != w:
+                warn("Model resolution and batch resolution differ, may produce unexpected results")
+            hs, ws = h, w
+            a_t, b_t = im_A, im_B
+        else:
+            raise ValueError(f"Unsupported input type: {type(im_A)=} and {type(im_B)=}")
+
+        with torch.cuda.device(eng.device):
+            images = torch.cat((a_t.to(eng.device, torch.float32, non_blocking=True),
+                                b_t.to(eng.device, torch.float32, non_blocking=True))).contiguous()
+            state, states, sizes = eng.run_pass(images, b, symmetric, False, scale_factor)
+            coarse = states[16] if self.attenuate_cert else None
+            hc, wc = sizes[16]
+            if self.upsample_preds:
+                hs_lo, ws_lo = hs, ws
+                hs, ws = self.upsample_res
+                if im_A_high_res is None and im_B_high_res is None:
+                    if isinstance(im_A_input, (str, os.PathLike)):
+                        hi_a, hi_b = Image.open(im_A_input).convert("RGB"), Image.open(im_B_input).convert("RGB")
+                    else:
+                        assert isinstance(im_A_input, Image.Image), f"Unsupported input type: {type(im_A_input)=}"
+                        assert isinstance(im_B_input, Image.Image), f"Unsupported input type: {type(im_B_input)=}"
+                        hi_a, hi_b = im_A_input, im_B_input
+                    a_h = pil_to_normalized(hi_a, (hs, ws))[None]
+                    b_h = pil_to_normalized(hi_b, (hs, ws))[None]
+                elif im_A_high_res is not None and im_B_high_res is not None:
+                    a_h, b_h = im_A_high_res, im_B_high_res
+                else:
+                    raise ValueError(f"Invalid upsample_preds and high_res inputs with {im_A=},{im_A_high_res=},{im_B=} and {im_B_high_res=}")
+                scale_factor = math.sqrt(self.upsample_res[0] * self.upsample_res[1] / (560 ** 2))
+                images_hi = torch.cat((a_h.to(eng.device, torch.float32, non_blocking=True),
+                                       b_h.to(eng.device, torch.float32, non_blocking=True))).contiguous()
+                hs, ws = images_hi.shape[-2:]
+                state, _, _ = eng.run_pass(images_hi, b, symmetric, True, scale_factor, (state, hs_lo, ws_lo))
+            warp, certainty = eng.epilogue(state, coarse, hc, wc, b, hs, ws, symmetric)
+        return warp, certainty
+
+    # ---- sampling (matcher.py:598-629) ----------------------------------------------------------------
+    def sample(self, matches, certainty, num=10000):
+        """Certainty-thresholded, density-balanced match sampling.  Both `torch.multinomial` draws are kept
+        (same RNG stream semantics as the reference); the 4*num x 4*num Gaussian KDE runs in
+        `romab200_kde_density` without materialising the matrix."""
+        if "threshold" in self.sample_mode:
+            upper_thresh = self.sample_thresh
+            certainty = certainty.clone()
+            certainty[certainty > upper_thresh] = 1
+        matches, certainty = matches.reshape(-1, 4), certainty.reshape(-1)
+        expansion_factor = 4 if "balanced" in self.sample_mode else 1
+        good_samples = torch.multinomial(certainty, num_samples=min(expansion_factor * num, len(certainty)), replacement=False)
+        good_matches, good_certainty = matches[good_samples], certainty[good_samples]
+        if "balanced" not in self.sample_mode:
+            return good_matches, good_certainty
+        if good_matches.device.type != "cuda":
+            raise RuntimeError("roma_b200.sample needs CUDA tensors (no CPU fallback)")
+        with torch.cuda.device(good_matches.device):
+            density = self.engine.kde(good_matches, std=0.1, half=True).to(torch.float16)   # kde.py: x.half()
+        p = 1 / (density + 1)
+        p[density < 10] = 1e-7      # at least ~10 perfect neighbours, as in the reference
+        balanced_samples = torch.multinomial(p, num_samples=min(num, len(good_certainty)), replacement=False)
+        return good_matches[balanced_samples], good_certainty[balanced_samples]
+
+    # ---- small geometry helpers (matcher.py:672-773) ---------------------------------------------------
+    def _to_pixel_coordinates(self, coords, H, W):
+        return torch.stack((W / 2 * (coords[..., 0] + 1), H / 2 * (coords[..., 1] + 1)), dim=-1)
+
+    def to_pixel_coordinates(self, coords, H_A, W_A, H_B=None, W_B=None):
+        if coords.shape[-1] == 2:
+            return self._to_pixel_coordinates(coords, H_A, W_A)
+        if isinstance(coords, (list, tuple)):
+            kpts_A, kpts_B = coords[0], coords[1]
+        else:
+            kpts_A, kpts_B = coords[..., :2], coords[..., 2:]
+        return self._to_pixel_coordinates(kpts_A, H_A, W_A), self._to_pixel_coordinates(kpts_B, H_B, W_B)
+
+    def to_normalized_coordinates(self, coords, H_A, W_A, H_B, W_B):
+        if isinstance(coords, (list, tuple)):
+            kpts_A, kpts_B = coords[0], coords[1]
+        else:
+            kpts_A, kpts_B = coords[..., :2], coords[..., 2:]
+        kpts_A = torch.stack((2 / W_A * kpts_A[..., 0] - 1, 2 / H_A * kpts_A[..., 1] - 1), dim=-1)
+        kpts_B = torch.stack((2 / W_B * kpts_B[..., 0] - 1, 2 / H_B * kpts_B[..., 1] - 1), dim=-1)
+        return kpts_A, kpts_B
+
+    def conf_from_fb_consistency(self, flow_forward, flow_backward, th=2):
+        has_batch = flow_forward.dim() != 3
+        if not has_batch:
+            flow_forward, flow_backward = flow_forward[None], flow_backward[None]
+        H, W = flow_forward.shape[-3:-1]
+        th_n = 2 * th / max(H, W)
+        xs = torch.linspace(-1 + 1 / W, 1 - 1 / W, W)
+        ys = torch.linspace(-1 + 1 / H, 1 - 1 / H, H)
+        coords = torch.stack(torch.meshgrid(xs, ys, indexing="xy"), dim=-1).to(flow_forward.device)
+        coords_fb = F.grid_sample(flow_backward.permute(0, 3, 1, 2), flow_forward, align_corners=False,
+                                  mode="bilinear").permute(0, 2, 3, 1)
+        in_th = ((coords - coords_fb).norm(dim=-1) < th_n).float()
+        return in_th if has_batch else in_th[0]
+
+    def match_keypoints(self, x_A, x_B, warp, certainty, return_tuple=True, return_inds=False, max_dist=0.005, cert_th=0):
+        x_A_to_B = F.grid_sample(warp[..., -2:].permute(2, 0, 1)[None], x_A[None, None], align_corners=False,
+                                 mode="bilinear")[0, :, 0].mT
+        cert_A_to_B = F.grid_sample(certainty[None, None, ...], x_A[None, None], align_corners=False,
+                                    mode="bilinear")[0, 0, 0]
+        D = torch.cdist(x_A_to_B, x_B)
+        mutual = (D == D.min(dim=-1, keepdim=True).values) * (D == D.min(dim=-2, keepdim=True).values)
+        inds_A, inds_B = torch.nonzero(mutual * (cert_A_to_B[:, None] > cert_th) * (D < max_dist), as_tuple=True)
+        if return_tuple:
+            return (inds_A, inds_B) if return_inds else (x_A[inds_A], x_B[inds_B])
+        if return_inds:
+            return torch.cat((inds_A, inds_B), dim=-1)
+        return torch.cat((x_A[inds_A], x_B[inds_B]), dim=-1)
+
+    def visualize_warp(self, warp, certainty, im_A=None, im_B=None, im_A_path=None, im_B_path=None, device="cuda",
+                       symmetric=True, save_path=None, unnormalize=False):
+        import numpy as np
+        H, W2, _ = warp.shape
+        W = W2 // 2 if symmetric else W2
+        if im_A is None:
+            im_A, im_B = Image.open(im_A_path).convert("RGB"), Image.open(im_B_path).convert("RGB")
+        if not isinstance(im_A, torch.Tensor):
+            im_A, im_B = im_A.resize((W, H)), im_B.resize((W, H))
+            x_B = (torch.tensor(np.array(im_B)) / 255).to(device).permute(2, 0, 1)
+            x_A = (torch.tensor(np.array(im_A)) / 255).to(device).permute(2, 0, 1) if symmetric else None
+        else:
+            x_A, x_B = (im_A if symmetric else None), im_B
+        im_A_transfer = F.grid_sample(x_B[None], warp[:, :W, 2:][None], mode="bilinear", align_corners=False)[0]
+        if symmetric:
+            im_B_transfer = F.grid_sample(x_A[None], warp[:, W:, :2][None], mode="bilinear", align_corners=False)[0]
+            warp_im = torch.cat((im_A_transfer, im_B_transfer), dim=2)
+            white_im = torch.ones((H, 2 * W), device=device)
+        else:
+            warp_im, white_im = im_A_transfer, torch.ones((H, W), device=device)
+        vis_im = certainty * warp_im + (1 - certainty) * white_im
+        if save_path is not None:
+            arr = vis_im
+            if unnormalize:
+                mean = torch.tensor([0.485, 0.456, 0.406], device=arr.device)[:, None, None]
+                std = torch.tensor([0.229, 0.224, 0.225], device=arr.device)[:, None, None]
+                arr = arr * std + mean
+            arr = (arr.clamp(0, 1) * 255).byte().permute(1, 2, 0).cpu().numpy()
+            Image.fromarray(arr).save(save_path)
+        return vis_im

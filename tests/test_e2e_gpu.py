@@ -1,0 +1,131 @@
+"""End-to-end parity of the CUDA path (fp32 parity mode) against the CPU oracle and the golden fixtures
+made from the unmodified reference.  North-star tolerance: 1e-4 max-abs on warp and certainty."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import load_golden  # noqa: E402
+from roma_b200 import synthetic  # noqa: E402
+
+TOL = 1e-4
+
+
+def build(weights, g, amp_dtype=torch.float32):
+    from roma_b200 import roma_outdoor
+    coarse, up, sym, upp = (int(v) for v in g["meta"][:4])
+    return roma_outdoor("cuda", weights=weights[0], dinov2_weights=weights[1], coarse_res=coarse,
+                        upsample_res=up or coarse, symmetric=bool(sym), upsample_preds=bool(upp), amp_dtype=amp_dtype)
+
+
+def report(name, warp, cert, g, step=1):
+    w = warp[:, ::step, ::step].float().cpu().numpy()
+    c = cert[:, ::step, ::step].float().cpu().numpy()
+    ew, ec = np.abs(w - g["warp"]).max(), np.abs(c - g["certainty"]).max()
+    print(f"[{name}] warp max-abs err {ew:.3e}  certainty max-abs err {ec:.3e}")
+    return ew, ec
+
+
+@pytest.mark.parametrize("name", ["small_sym_up", "small_nosym_up", "small_sym_noup", "small_b2_sym_up"])
+def test_match_small_vs_reference_golden(weights, name):
+    g = load_golden(name)
+    coarse, up, sym, upp, batch, seed, step = (int(v) for v in g["meta"])
+    model = build(weights, g)
+    A, B, Ah, Bh = synthetic.make_pair(batch, coarse, up if upp else None, seed)
+    warp, cert = model.match(A.cuda(), B.cuda(), im_A_high_res=None if Ah is None else Ah.cuda(),
+                             im_B_high_res=None if Bh is None else Bh.cuda())
+    assert warp.shape == g["warp"].shape and cert.shape == g["certainty"].shape
+    assert warp.dtype == torch.float32 and cert.dtype == torch.float32 and warp.is_cuda
+    ew, ec = report(name, warp, cert, g)
+    assert ew <= TOL and ec <= TOL
+
+
+def test_stagewise_vs_reference_hooks(weights):
+    """Stage tensors of the coarse pass against the tensors hooked out of the reference's own modules."""
+    g = load_golden("small_sym_up")
+    model = build(weights, g)
+    model.engine.debug = {}
+    A, B, Ah, Bh = synthetic.make_pair(1, 112, 168, 1)
+    model.match(A.cuda(), B.cuda(), im_A_high_res=Ah.cuda(), im_B_high_res=Bh.cuda())
+    dbg = model.engine.debug
+    model.engine.debug = None
+
+    def err(ours, ref):
+        return float((ours.float().cpu() - torch.from_numpy(ref)).abs().max())
+    errs = {}
+    for s in (16, 8, 4, 2, 1):
+        errs[f"proj{s}"] = err(dbg[f"lo.proj{s}"].permute(0, 3, 1, 2), g[f"proj{s}"])
+        errs[f"delta{s}"] = err(dbg[f"lo{s}.delta"].permute(0, 3, 1, 2), g[f"delta{s}"])
+    n = 64
+    errs["gp_mu"] = err(dbg["gp.mu"].transpose(1, 2).reshape(2, 512, 8, 8), g["gp_mu"])
+    errs["cls"] = err(dbg["cls"].transpose(1, 2).reshape(2, 4097, 8, 8), g["cls_and_cert"])
+    print({k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["proj16"] < 2e-4 and errs["gp_mu"] < 1e-4 and errs["cls"] < 5e-3
+    for s in (16, 8, 4, 2, 1):
+        assert errs[f"proj{s}"] < 2e-4 and errs[f"delta{s}"] < 2e-3, (s, errs)
+
+
+def test_match_pil_route(weights):
+    g = load_golden("small_pil_sym_up")
+    model = build(weights, g)
+    a, b = synthetic.make_pil_pair(int(g["meta"][5]))
+    warp, cert = model.match(a, b)
+    ew, ec = report("pil", warp, cert, g)
+    assert ew <= TOL and ec <= TOL
+
+
+def test_api_errors_and_forward(weights):
+    g = load_golden("small_sym_up")
+    model = build(weights, g)
+    A, B, Ah, Bh = synthetic.make_pair(1, 112, 168, 1)
+    with pytest.raises(ValueError):
+        model.match(A.cuda(), B.cuda(), batched=False)
+    with pytest.raises(AssertionError):
+        model.match(torch.zeros(1, 3, 100, 112).cuda(), B.cuda())
+    with pytest.raises(AssertionError):          # tensors + upsample_preds need *_high_res (matcher.py:863-866)
+        model.match(A.cuda(), B.cuda())
+    with pytest.raises(ValueError):
+        model.match(A.cuda(), B.cuda(), im_A_high_res=Ah.cuda())
+    with pytest.raises(ValueError):          # mixed input types (matcher.py:828)
+        model.match(A.cuda(), synthetic.make_pil_pair(3)[0])
+    corr = model.forward_symmetric({"im_A": A.cuda(), "im_B": B.cuda()}, scale_factor=112 / 560)
+    assert sorted(corr) == [1, 2, 4, 8, 16]
+    assert corr[1]["flow"].shape == (2, 2, 112, 112) and corr[16]["certainty"].shape == (2, 1, 8, 8)
+    model.symmetric = False
+    model.upsample_preds = False
+    warp, cert = model.match(A.cuda(), B.cuda(), 1, 2, 3)     # extra positional args are ignored
+    assert warp.shape == (1, 112, 112, 4) and cert.shape == (1, 112, 112)
+    assert model.get_output_resolution() == (112, 112)
+    kp = model.to_pixel_coordinates(warp[0, :2, :2], 100, 200, 300, 400)
+    assert kp[0].shape == (2, 2, 2)
+
+
+def test_sample_statistics(weights):
+    """sample(): same draws as the reference are impossible (different KDE rounding feeds the second
+    multinomial), so check the contract: shapes, membership, certainty thresholding and density balancing."""
+    g = load_golden("small_sym_up")
+    model = build(weights, g)
+    warp = torch.from_numpy(g["warp"]).cuda()
+    cert = torch.from_numpy(g["certainty"]).cuda()
+    torch.manual_seed(0)
+    m, c = model.sample(warp[0], cert[0], num=500)
+    assert m.shape == (500, 4) and c.shape == (500,)
+    flat = warp[0].reshape(-1, 4)
+    # every sampled match is a row of the warp
+    d = torch.cdist(m, flat).min(dim=1).values
+    assert d.max().item() < 1e-6
+    assert ((c == 1) | (c <= model.sample_thresh)).all()
+
+
+@pytest.mark.slow
+def test_match_full_vs_reference_golden(weights):
+    """560 -> 864 (BASELINE config 2 workload) against the sub-sampled reference output."""
+    g = load_golden("full_sym_up")
+    model = build(weights, g)
+    A, B, Ah, Bh = synthetic.make_pair(1, 560, 864, 1)
+    warp, cert = model.match(A.cuda(), B.cuda(), im_A_high_res=Ah.cuda(), im_B_high_res=Bh.cuda())
+    assert warp.shape == (1, 864, 1728, 4)
+    ew, ec = report("full", warp, cert, g, step=8)
+    assert ew <= TOL and ec <= TOL
+    model.engine.free_buffers()
