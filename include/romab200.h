@@ -33,6 +33,8 @@ enum rb_backend { RB_BACKEND_AUTO = 0, RB_BACKEND_SIMT = 1, RB_BACKEND_TCGEN05 =
 
 int romab200_abi_version(void);
 const char* romab200_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process */
+unsigned long long romab200_launch_count(void);
 /* 1 if the running device is sm_100 (B200) and the tcgen05/TMA kernels may be launched */
 int romab200_device_ok(void);
 

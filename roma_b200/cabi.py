@@ -80,6 +80,7 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
     lib.romab200_last_error.restype = ctypes.c_char_p
     lib.romab200_abi_version.restype = ctypes.c_int
     lib.romab200_device_ok.restype = ctypes.c_int
+    lib.romab200_launch_count.restype = ctypes.c_ulonglong
     for fn in FUNCTIONS:
         getattr(lib, fn)            # AttributeError if the header declares a symbol the library lacks
     _lib = lib
@@ -122,6 +123,11 @@ def call(fn_name: str, struct_name: str, **kw) -> None:
     launch_count += 1
     if rc != 0:
         raise RuntimeError(f"{fn_name} failed: {lib.romab200_last_error().decode()}")
+
+
+def kernel_launches() -> int:
+    """Kernels launched by libromab200 in this process so far."""
+    return int(load_library().romab200_launch_count())
 
 
 def device_ok() -> bool:

@@ -5,6 +5,7 @@
 namespace rb {
 
 static thread_local char g_error[512] = "";
+static unsigned long long g_launches = 0;     // kernels launched by this library (every launch goes through check_launch)
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -14,6 +15,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int check_launch(const char* what) {
+    ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
@@ -26,6 +28,7 @@ int check_launch(const char* what) {
 
 extern "C" int romab200_abi_version(void) { return ROMAB200_ABI_VERSION; }
 extern "C" const char* romab200_last_error(void) { return rb::g_error; }
+extern "C" unsigned long long romab200_launch_count(void) { return rb::g_launches; }
 
 extern "C" int romab200_device_ok(void) {
     int dev = 0;

@@ -1,10 +1,342 @@
-// tcgen05 / TMA GEMM back-end (16-bit operands, fp32 accumulation in TMEM).  Placeholder until the
-// kernel lands: refuses loudly instead of falling back.
+// tcgen05 / TMA GEMM back-end of romab200_gemm: fp16 / bf16 operands, fp32 accumulation in TMEM.
+//
+// One CTA computes one 128 x BN output tile (BN in {32, 64, 128, 256}).  Warp roles:
+//   warp 0      TMA producer: one elected lane issues cp.async.bulk.tensor loads of the A (128 x 64) and
+//               B (BN x 64, or 64 x BN when B is [K,N]) tiles into a STAGES-deep 128B-swizzled smem ring;
+//   warp 1      allocates TMEM, then one elected lane issues tcgen05.mma (cta_group::1, kind::f16,
+//               M=128, N=BN, K=16 per instruction, 4 per stage) and tcgen05.commit to free ring slots;
+//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator (each warp owns the 32 TMEM lanes it may
+//               address), apply the shared fused epilogue, store rows with 16-byte vector stores.
+// A-operand "taps" (the 9 shifted row blocks of a 3x3 convolution on a zero-padded channels-last map) are
+// just a per-k-block row offset on the TMA coordinate; out-of-range rows/columns are zero-filled by TMA,
+// which also handles M/N/K tails, so no operand is ever padded or copied.
+// Batched GEMMs (attention heads) use the 3rd/4th tensor-map dimension.
 #include "common.cuh"
+#include <cuda.h>
+
 namespace rb {
-int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
-    (void)stream;
-    set_error("gemm: tcgen05 back-end not built yet (dtype_ab=%d)", a->dtype_ab);
-    return 1;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 |
+// layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct TcParams {
+    int M, N, K;
+    int batch1;
+    int ntaps, k_per_tap; int tap_rows[9];
+    int trans_b, is_bf16;
+    int64_t sc0, sc1, sr0, sr1, sna0, snb0;
+    Epilogue epi;
+};
+
+constexpr int TC_BM = 128, TC_BK = 64;
+
+template <int BN> struct TcCfg {
+    static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);   // BN<=128: ~96 KB -> 2 CTAs / SM
+    static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+    static constexpr int B_BYTES = BN * TC_BK * 2;
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                         const TcParams p) {
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+    const int z = blockIdx.z, z0 = z / p.batch1, z1 = z % p.batch1;
+    const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const int kb_per_tap = p.ntaps > 1 ? p.k_per_tap / TC_BK : kblocks;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
+                int tap = 0, kin = kb * TC_BK, shift = 0;
+                if (p.ntaps > 1) { tap = kb / kb_per_tap; kin = (kb - tap * kb_per_tap) * TC_BK; shift = p.tap_rows[tap]; }
+                tma_load_4d(sA + s * Cfg::A_BYTES, &map_a, &full_bar[s], kin, m0 + shift, z1, z0);
+                if (!p.trans_b) {
+                    tma_load_4d(sB + s * Cfg::B_BYTES, &map_b, &full_bar[s], kb * TC_BK, n0, z1, z0);
+                } else {
+                    // B is [K, N]: boxes of 64 (n) x 64 (k); one box per 64 columns of the tile
+#pragma unroll
+                    for (int j = 0; j < (BN + 63) / 64; ++j)
+                        tma_load_4d(sB + s * Cfg::B_BYTES + j * (64 * 128), &map_b, &full_bar[s], n0 + j * 64, kb * TC_BK, z1, z0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A/B = f16|bf16, A K-major, B K-major or MN-major, N>>3, M>>4
+            uint32_t idesc = 0;
+            idesc |= 1u << 4;
+            idesc |= (uint32_t)(p.is_bf16 ? 1 : 0) << 7;
+            idesc |= (uint32_t)(p.is_bf16 ? 1 : 0) << 10;
+            idesc |= (uint32_t)(p.trans_b ? 1 : 0) << 16;
+            idesc |= (uint32_t)(BN >> 3) << 17;
+            idesc |= (uint32_t)(TC_BM >> 4) << 24;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
+                const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                    // K-major SW128: 8-row groups are 1024 B apart (SBO); a K step of 16 elements = +32 B inside the atom
+                    uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, 1024);
+                    uint64_t bdesc = p.trans_b ? make_smem_desc(b_addr + k * 2048, 64 * 128, 1024)     // MN-major: +2 k-groups
+                                               : make_smem_desc(b_addr + k * 32, 16, 1024);
+                    umma_f16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);          // frees the smem slot when these MMAs retire
+            }
+            umma_commit(tmem_full_bar);              // accumulator complete
+        }
+    } else {
+        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        Epilogue e = p.epi;
+        e.C = (char*)e.C + (z0 * p.sc0 + z1 * p.sc1) * dtype_size(e.dtype_c);
+        if (e.R) e.R = (const char*)e.R + (z0 * p.sr0 + z1 * p.sr1) * dtype_size(e.dtype_r);
+        if (e.norm_a) e.norm_a += z0 * p.sna0;
+        if (e.norm_b) e.norm_b += z0 * p.snb0;
+        const int m = m0 + q * 32 + lane;
+        const int64_t orow = m < p.M ? e.map_row(m) : -1;
+        const bool vec_ok = (e.ldc * dtype_size(e.dtype_c)) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.C) % 16 == 0);
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 32) {
+            if (n0 + cb >= p.N) break;                     // warp-uniform
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cb, v);
+            if (orow < 0) continue;
+            const int nb = n0 + cb;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (nb + j < p.N) ? e.apply(v[j], m, nb + j, orow) : 0.f;
+            if (vec_ok && nb + 32 <= p.N) {
+                if (e.dtype_c == RB_F32) {
+                    float4* dst = reinterpret_cast<float4*>((float*)e.C + orow * e.ldc + nb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+                    uint4* dst = reinterpret_cast<uint4*>((uint16_t*)e.C + orow * e.ldc + nb);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            float lo = v[8 * j + 2 * t], hi = v[8 * j + 2 * t + 1];
+                            if (e.dtype_c == RB_F16) { __half2 h = __floats2half2_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
+                            else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
+                        }
+                        dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (nb + j < p.N) store_any(e.C, orow * e.ldc + nb + j, e.dtype_c, v[j]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || !ptr) return nullptr;
+        fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// 4-D map over (inner, rows, batch1, batch0) of a 16-bit matrix
+static int make_map(CUtensorMap* map, const void* base, int is_bf16, uint64_t inner, uint64_t rows, uint64_t pitch_elems, uint64_t b1,
+                    uint64_t s1_elems, uint64_t b0, uint64_t s0_elems, uint32_t box_inner, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    RB_REQUIRE(enc, "gemm_tc: cuTensorMapEncodeTiled not available (driver too old?)");
+    RB_REQUIRE(((uintptr_t)base) % 16 == 0 && (pitch_elems * 2) % 16 == 0, "gemm_tc: operand base/pitch must be 16-byte aligned (pitch %llu elems)", (unsigned long long)pitch_elems);
+    RB_REQUIRE((b1 <= 1 || (s1_elems * 2) % 16 == 0) && (b0 <= 1 || (s0_elems * 2) % 16 == 0), "gemm_tc: batch strides must be 16-byte aligned");
+    cuuint64_t dims[4] = {inner, rows, b1 > 0 ? b1 : 1, b0 > 0 ? b0 : 1};
+    cuuint64_t strides[3] = {pitch_elems * 2, (b1 > 1 ? s1_elems : pitch_elems * rows) * 2, (b0 > 1 ? s0_elems : pitch_elems * rows) * 2};
+    cuuint32_t box[4] = {box_inner, box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RB_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed with %d (inner=%llu rows=%llu pitch=%llu)", (int)r,
+               (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)pitch_elems);
+    return 0;
+}
+
+template <int BN>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int zdim, cudaStream_t st) {
+    using Cfg = TcCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        RB_REQUIRE(e == cudaSuccess, "gemm_tc: cannot set %d bytes of dynamic shared memory: %s", Cfg::SMEM, cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.N + BN - 1) / BN, zdim);
+    gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM, st>>>(ma, mb, p);
+    return check_launch("gemm_tc");
+}
+
+int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
+    RB_REQUIRE(a->dtype_ab == RB_F16 || a->dtype_ab == RB_BF16, "gemm_tc: operands must be fp16/bf16 (got %d)", a->dtype_ab);
+    RB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "gemm_tc: empty problem");
+    TcParams p;
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.batch1 = a->batch1 > 0 ? a->batch1 : 1;
+    const int batch0 = a->batch0 > 0 ? a->batch0 : 1;
+    p.ntaps = a->ntaps > 1 ? a->ntaps : 1;
+    p.k_per_tap = a->K / p.ntaps;
+    for (int i = 0; i < 9; ++i) p.tap_rows[i] = a->tap_rows[i];
+    p.trans_b = a->trans_b; p.is_bf16 = a->dtype_ab == RB_BF16;
+    p.sc0 = a->sc0; p.sc1 = a->sc1; p.sr0 = a->sr0; p.sr1 = a->sr1; p.sna0 = a->sna0; p.snb0 = a->snb0;
+    p.epi = make_epilogue(a);
+    if (p.ntaps > 1) {
+        RB_REQUIRE(a->K % p.ntaps == 0 && p.k_per_tap % TC_BK == 0, "gemm_tc: K/ntaps=%d must be a multiple of %d", p.k_per_tap, TC_BK);
+        RB_REQUIRE(!a->trans_b && batch0 * p.batch1 == 1, "gemm_tc: taps need un-batched [N,K] weights");
+    }
+    const int zdim = batch0 * p.batch1;
+    RB_REQUIRE(zdim <= 65535, "gemm_tc: batch too large");
+    const int64_t a_rows = a->a_rows > 0 ? a->a_rows : a->M;
+    int BN = a->N <= 32 && !a->trans_b ? 32 : (a->N <= 64 ? 64 : (a->N <= 128 || a->trans_b ? 128 : 256));
+    // very tall-skinny K: keep 128-wide tiles so that more CTAs are in flight
+    if (BN == 256 && ((int64_t)((a->M + 127) / 128) * ((a->N + 255) / 256) * zdim) < 148) BN = 128;
+    CUtensorMap ma, mb;
+    if (make_map(&ma, a->A, p.is_bf16, p.ntaps > 1 ? p.k_per_tap : a->K, a_rows, a->lda, p.batch1, a->sa1, batch0, a->sa0, TC_BK, TC_BM)) return 1;
+    if (!a->trans_b) {
+        if (make_map(&mb, a->B, p.is_bf16, a->K, a->N, a->ldb, p.batch1, a->sb1, batch0, a->sb0, TC_BK, BN)) return 1;
+    } else {
+        if (make_map(&mb, a->B, p.is_bf16, a->N, a->K, a->ldb, p.batch1, a->sb1, batch0, a->sb0, 64, TC_BK)) return 1;
+    }
+    switch (BN) {
+        case 32: return launch_tc<32>(ma, mb, p, zdim, stream);
+        case 64: return launch_tc<64>(ma, mb, p, zdim, stream);
+        case 128: return launch_tc<128>(ma, mb, p, zdim, stream);
+        default: return launch_tc<256>(ma, mb, p, zdim, stream);
+    }
+}
+
 }  // namespace rb

@@ -20,6 +20,7 @@ together as a 3-channel fp32 state map [D, h, w, 3].
 from __future__ import annotations
 
 import math
+from contextlib import contextmanager
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -49,6 +50,20 @@ class Engine:
         self._buf: Dict[tuple, torch.Tensor] = {}
         self._const: Dict[tuple, torch.Tensor] = {}
         self.debug: Optional[dict] = None        # set to {} to keep stage tensors (tests)
+        self.profile: Optional[dict] = None      # set to {} to collect CUDA-event timings per stage (bench.py)
+        self.gemm_profile: Optional[list] = None  # set to [] to time every GEMM launch: (backend, flops, start, end)
+
+    @contextmanager
+    def stage(self, name):
+        """CUDA-event bracket on the launch stream around one stage of the pipeline (no-op unless profiling)."""
+        if self.profile is None:
+            yield
+            return
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        yield
+        end.record()
+        self.profile.setdefault(name, []).append((start, end))
 
     # ------------------------------------------------------------------ buffers and constants
     def buf(self, name, shape, dtype=None, zero=False):
@@ -111,7 +126,15 @@ class Engine:
                     dtype_c=self.dt if dtype_c is None else dtype_c,
                     batch0=1, batch1=1, ntaps=1, alpha=1.0)
         args.update(kw)
+        if self.gemm_profile is None:
+            call("romab200_gemm", "rb_gemm_args", **args)
+            return
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
         call("romab200_gemm", "rb_gemm_args", **args)
+        end.record()
+        flops = 2.0 * M * N * K * args["batch0"] * args["batch1"]
+        self.gemm_profile.append(("simt" if args["dtype_ab"] == cabi.RB_F32 else "tcgen05", flops, start, end))
 
     def layernorm(self, x, y, gb, rows, cols, eps, dtype_y=None):
         call("romab200_layernorm", "rb_layernorm_args", x=x, y=y, gamma=gb[0], beta=gb[1], rows=rows, cols=cols,
@@ -164,10 +187,10 @@ class Engine:
         ld = 3 * dim
         es = qkv.element_size()
         q_ptr, k_ptr, v_ptr = qkv.data_ptr(), qkv.data_ptr() + dim * es, qkv.data_ptr() + 2 * dim * es
-        self.gemm(q_ptr, k_ptr, S, N, N, d, ld, ld, npad, batch0=Bn, batch1=heads,
+        # the 1/sqrt(d) scale rides on the QK^T epilogue so that 16-bit scores cannot overflow
+        self.gemm(q_ptr, k_ptr, S, N, N, d, ld, ld, npad, batch0=Bn, batch1=heads, alpha=1.0 / math.sqrt(d),
                   sa0=N * ld, sa1=d, sb0=N * ld, sb1=d, sc0=heads * N * npad, sc1=N * npad)
-        call("romab200_softmax_rows", "rb_softmax_args", s=S, rows=Bn * heads * N, cols=N, lds=npad, dtype=self.dt,
-             scale=1.0 / math.sqrt(d))
+        call("romab200_softmax_rows", "rb_softmax_args", s=S, rows=Bn * heads * N, cols=N, lds=npad, dtype=self.dt, scale=1.0)
         self.gemm(S, v_ptr, out, N, d, N, npad, ld, dim, trans_b=1, batch0=Bn, batch1=heads,
                   sa0=heads * N * npad, sa1=N * npad, sb0=N * ld, sb1=d, sc0=N * dim, sc1=d)
 
@@ -332,14 +355,17 @@ class Engine:
         E = 2 * b
         D = E if symmetric else b
         _, _, H, W = images.shape
-        taps = self.vgg(images, tag)
+        with self.stage(f"vgg.{tag}"):
+            taps = self.vgg(images, tag)
         sizes = {s: (taps[s][1], taps[s][2]) for s in (1, 2, 4, 8)}
         states = {}
         if not upsample:
-            feat16_raw, hp, wp = self.dinov2(images)
+            with self.stage("dinov2"):
+                feat16_raw, hp, wp = self.dinov2(images)
             sizes[16] = (hp, wp)
             state = self.buf("state.lo.16", (D, hp, wp, 3), dtype=torch.float32)
-            feat16 = self.coarse_match(feat16_raw, E, D, b, hp, wp, state)
+            with self.stage("gp+decoder"):
+                feat16 = self.coarse_match(feat16_raw, E, D, b, hp, wp, state)
             if self.debug is not None:
                 self.debug["coarse_state"] = state.clone()
             scales = arch.SCALES
@@ -352,11 +378,13 @@ class Engine:
             if s == 16:
                 feat, ldf = feat16, arch.PROJ[16][1]
             else:
-                feat = self.proj_from_padded(s, taps[s][0], E, h, w, tag)
+                with self.stage(f"proj{s}.{tag}"):
+                    feat = self.proj_from_padded(s, taps[s][0], E, h, w, tag)
                 ldf = pad8(arch.PROJ[s][1])
             if self.debug is not None:
                 self.debug[f"{tag}.proj{s}"] = feat.view(E, h, w, -1)[..., :arch.PROJ[s][1]].float().clone()
-            self.refine(s, feat, ldf, E, D, b, h, w, state, scale_factor, H, W, f"{tag}{s}")
+            with self.stage(f"refine{s}.{tag}"):
+                self.refine(s, feat, ldf, E, D, b, h, w, state, scale_factor, H, W, f"{tag}{s}")
             if keep_states or s == 16:
                 states[s] = state.clone() if keep_states else state
             if s != 1:

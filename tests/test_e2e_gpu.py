@@ -111,10 +111,9 @@ def test_sample_statistics(weights):
     torch.manual_seed(0)
     m, c = model.sample(warp[0], cert[0], num=500)
     assert m.shape == (500, 4) and c.shape == (500,)
-    flat = warp[0].reshape(-1, 4)
-    # every sampled match is a row of the warp
-    d = torch.cdist(m, flat).min(dim=1).values
-    assert d.max().item() < 1e-6
+    # every sampled match is (bit-exactly) a row of the warp
+    rows = {tuple(r) for r in warp[0].reshape(-1, 4).cpu().numpy().view("uint32").tolist()}
+    assert all(tuple(r) in rows for r in m.cpu().numpy().view("uint32").tolist())
     assert ((c == 1) | (c <= model.sample_thresh)).all()
 
 
@@ -129,3 +128,21 @@ def test_match_full_vs_reference_golden(weights):
     ew, ec = report("full", warp, cert, g, step=8)
     assert ew <= TOL and ec <= TOL
     model.engine.free_buffers()
+
+
+@pytest.mark.parametrize("amp", [torch.float16, torch.bfloat16])
+def test_match_fast_mode_small(weights, amp):
+    """16-bit tensor-core mode (the reference's CUDA autocast regime).  Two fp16 implementations do not agree to
+    1e-4 end to end (argmax flips of the coarse classifier move single pixels by a whole anchor), so
+    the bar here is statistical: the bulk of the warp agrees closely and outliers are rare."""
+    g = load_golden("small_sym_up")
+    model = build(weights, g, amp_dtype=amp)
+    A, B, Ah, Bh = synthetic.make_pair(1, 112, 168, 1)
+    warp, cert = model.match(A.cuda(), B.cuda(), im_A_high_res=Ah.cuda(), im_B_high_res=Bh.cuda())
+    ew = np.abs(warp.cpu().numpy() - g["warp"]).max(-1)
+    ec = np.abs(cert.cpu().numpy() - g["certainty"])
+    print(f"[fast {amp}] warp err: median {np.median(ew):.2e} p99 {np.percentile(ew, 99):.2e} max {ew.max():.2e} "
+          f"frac>1e-2 {np.mean(ew > 1e-2):.4f}; cert err median {np.median(ec):.2e} max {ec.max():.2e}")
+    assert np.isfinite(ew).all() and np.isfinite(ec).all()
+    tol_med = 2e-3 if amp == torch.float16 else 1e-2
+    assert np.median(ew) < tol_med and np.mean(ew > 5e-2) < 0.05
