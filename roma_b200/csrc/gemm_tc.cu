@@ -83,6 +83,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 consecutive floats of a row vector (bias / LayerScale / residual): 8 x 16-byte loads when possible
+__device__ __forceinline__ void load_row32(const float* __restrict__ p, float* out, bool full, int remaining) {
+    if (full && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 t = reinterpret_cast<const float4*>(p)[j];
+            out[4 * j] = t.x; out[4 * j + 1] = t.y; out[4 * j + 2] = t.z; out[4 * j + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) out[j] = j < remaining ? p[j] : 0.f;
+    }
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 |
 // layout SWIZZLE_128B (2) << 61
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -101,6 +115,7 @@ struct TcParams {
     int batch1;
     int ntaps, k_per_tap; int tap_rows[9];
     int trans_b, is_bf16;
+    int tiles_m, tiles_n, total_tiles;
     int64_t sc0, sc1, sr0, sr1, sna0, snb0;
     Epilogue epi;
 };
@@ -109,12 +124,20 @@ constexpr int TC_BM = 128, TC_BK = 64;
 
 template <int BN> struct TcCfg {
     static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);   // BN<=128: ~96 KB -> 2 CTAs / SM
+    static constexpr int CTAS_PER_SM = BN >= 256 ? 1 : 2;
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // two accumulator stages
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent kernel: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (m fastest, so CTAs that run
+// together share the same weight tile in L2).  The accumulator is double-buffered in TMEM: the MMA warp starts the
+// next tile while the epilogue warps drain the previous one.
 template <int BN>
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                          const TcParams p) {
@@ -126,17 +149,17 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + STAGES;       // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
-    const int z = blockIdx.z, z0 = z / p.batch1, z1 = z % p.batch1;
     const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+    const int tiles_per_z = p.tiles_m * p.tiles_n;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -149,21 +172,27 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         // ===== TMA producer =====
         if (lane == 0) {
             const int kb_per_tap = p.ntaps > 1 ? p.k_per_tap / TC_BK : kblocks;
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
-                int tap = 0, kin = kb * TC_BK, shift = 0;
-                if (p.ntaps > 1) { tap = kb / kb_per_tap; kin = (kb - tap * kb_per_tap) * TC_BK; shift = p.tap_rows[tap]; }
-                tma_load_4d(sA + s * Cfg::A_BYTES, &map_a, &full_bar[s], kin, m0 + shift, z1, z0);
-                if (!p.trans_b) {
-                    tma_load_4d(sB + s * Cfg::B_BYTES, &map_b, &full_bar[s], kb * TC_BK, n0, z1, z0);
-                } else {
-                    // B is [K, N]: boxes of 64 (n) x 64 (k); one box per 64 columns of the tile
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int z = tile / tiles_per_z, r = tile - z * tiles_per_z;
+                const int nt = r / p.tiles_m, mt = r - nt * p.tiles_m;
+                const int m0 = mt * TC_BM, n0 = nt * BN, z0 = z / p.batch1, z1 = z - z0 * p.batch1;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
+                    int tap = 0, kin = kb * TC_BK, shift = 0;
+                    if (p.ntaps > 1) { tap = kb / kb_per_tap; kin = (kb - tap * kb_per_tap) * TC_BK; shift = p.tap_rows[tap]; }
+                    tma_load_4d(sA + s * Cfg::A_BYTES, &map_a, &full_bar[s], kin, m0 + shift, z1, z0);
+                    if (!p.trans_b) {
+                        tma_load_4d(sB + s * Cfg::B_BYTES, &map_b, &full_bar[s], kb * TC_BK, n0, z1, z0);
+                    } else {
+                        // B is [K, N]: boxes of 64 (n) x 64 (k); one box per 64 columns of the tile
 #pragma unroll
-                    for (int j = 0; j < (BN + 63) / 64; ++j)
-                        tma_load_4d(sB + s * Cfg::B_BYTES + j * (64 * 128), &map_b, &full_bar[s], n0 + j * 64, kb * TC_BK, z1, z0);
+                        for (int j = 0; j < (BN + 63) / 64; ++j)
+                            tma_load_4d(sB + s * Cfg::B_BYTES + j * (64 * 128), &map_b, &full_bar[s], n0 + j * 64, kb * TC_BK, z1, z0);
+                    }
                 }
             }
         }
@@ -178,73 +207,137 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             idesc |= (uint32_t)(p.trans_b ? 1 : 0) << 16;
             idesc |= (uint32_t)(BN >> 3) << 17;
             idesc |= (uint32_t)(TC_BM >> 4) << 24;
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);          // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
-                const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
-                    // K-major SW128: 8-row groups are 1024 B apart (SBO); a K step of 16 elements = +32 B inside the atom
-                    uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, 1024);
-                    uint64_t bdesc = p.trans_b ? make_smem_desc(b_addr + k * 2048, 64 * 128, 1024)     // MN-major: +2 k-groups
-                                               : make_smem_desc(b_addr + k * 32, 16, 1024);
-                    umma_f16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0);
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        // K-major SW128: 8-row groups are 1024 B apart (SBO); a K step of 16 elements = +32 B inside the atom
+                        uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, 1024);
+                        uint64_t bdesc = p.trans_b ? make_smem_desc(b_addr + k * 2048, 64 * 128, 1024)     // MN-major: +2 k-groups
+                                                   : make_smem_desc(b_addr + k * 32, 16, 1024);
+                        umma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);          // frees the smem slot when these MMAs retire
                 }
-                umma_commit(&empty_bar[s]);          // frees the smem slot when these MMAs retire
+                umma_commit(&tmem_full_bar[acc]);        // accumulator complete
             }
-            umma_commit(tmem_full_bar);              // accumulator complete
         }
     } else {
         // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        Epilogue e = p.epi;
-        e.C = (char*)e.C + (z0 * p.sc0 + z1 * p.sc1) * dtype_size(e.dtype_c);
-        if (e.R) e.R = (const char*)e.R + (z0 * p.sr0 + z1 * p.sr1) * dtype_size(e.dtype_r);
-        if (e.norm_a) e.norm_a += z0 * p.sna0;
-        if (e.norm_b) e.norm_b += z0 * p.snb0;
-        const int m = m0 + q * 32 + lane;
-        const int64_t orow = m < p.M ? e.map_row(m) : -1;
-        const bool vec_ok = (e.ldc * dtype_size(e.dtype_c)) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.C) % 16 == 0);
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+            const int z = tile / tiles_per_z, r = tile - z * tiles_per_z;
+            const int nt = r / p.tiles_m, mt = r - nt * p.tiles_m;
+            const int m0 = mt * TC_BM, n0 = nt * BN, z0 = z / p.batch1, z1 = z - z0 * p.batch1;
+            const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
+            mbar_wait(&tmem_full_bar[acc], acc_ph);
+            tc_fence_after();
+            Epilogue e = p.epi;
+            e.C = (char*)e.C + (z0 * p.sc0 + z1 * p.sc1) * dtype_size(e.dtype_c);
+            if (e.R) e.R = (const char*)e.R + (z0 * p.sr0 + z1 * p.sr1) * dtype_size(e.dtype_r);
+            if (e.norm_a) e.norm_a += z0 * p.sna0;
+            if (e.norm_b) e.norm_b += z0 * p.snb0;
+            const int m = m0 + q * 32 + lane;
+            const int64_t orow = m < p.M ? e.map_row(m) : -1;
+            const bool vec_ok = (e.ldc * dtype_size(e.dtype_c)) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.C) % 16 == 0);
 #pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 32) {
-            if (n0 + cb >= p.N) break;                     // warp-uniform
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cb, v);
-            if (orow < 0) continue;
-            const int nb = n0 + cb;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (nb + j < p.N) ? e.apply(v[j], m, nb + j, orow) : 0.f;
-            if (vec_ok && nb + 32 <= p.N) {
-                if (e.dtype_c == RB_F32) {
-                    float4* dst = reinterpret_cast<float4*>((float*)e.C + orow * e.ldc + nb);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int cb = 0; cb < BN; cb += 32) {
+                if (n0 + cb >= p.N) break;                     // warp-uniform
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cb, v);
+                if (orow < 0) continue;
+                const int nb = n0 + cb;
+                const bool full = nb + 32 <= p.N;
+                // every branch below is warp-uniform: the per-element work is straight-line code
+                if (e.epi == RB_EPI_COSKERNEL) {
+                    const float na = e.norm_a[m];
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = nb + j;
+                        const float pn = na * (n < p.N ? e.norm_b[n] : 1.f);
+                        const float sc = e.cos_normalized ? pn / (pn + e.eps) : 1.0f / (pn + e.eps);
+                        float r = expf((v[j] * sc - 1.0f) * e.inv_t);
+                        if (m == n) r += e.diag_add;
+                        v[j] = r;
+                    }
                 } else {
-                    uint4* dst = reinterpret_cast<uint4*>((uint16_t*)e.C + orow * e.ldc + nb);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            float lo = v[8 * j + 2 * t], hi = v[8 * j + 2 * t + 1];
-                            if (e.dtype_c == RB_F16) { __half2 h = __floats2half2_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
-                            else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
+                    if (e.alpha != 1.0f) {
+    #pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
+                    }
+                    if (e.bias) {
+                        float bv[32];
+                        load_row32(e.bias + nb, bv, full, p.N - nb);
+    #pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += bv[j];
+                    }
+                    if (e.act == RB_ACT_RELU) {
+    #pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (e.act == RB_ACT_GELU) {
+    #pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    }
+                    if (e.col_scale) {
+                        float sv[32];
+                        load_row32(e.col_scale + nb, sv, full, p.N - nb);
+    #pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= sv[j];
+                    }
+                    if (e.R) {
+                        if (e.dtype_r == RB_F32) {
+                            float rv[32];
+                            load_row32((const float*)e.R + orow * e.ldr + nb, rv, full, p.N - nb);
+    #pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += rv[j];
+                        } else {
+    #pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nb + j < p.N) v[j] += load_any(e.R, orow * e.ldr + nb + j, e.dtype_r);
                         }
-                        dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (nb + j < p.N) store_any(e.C, orow * e.ldc + nb + j, e.dtype_c, v[j]);
+                if (vec_ok && nb + 32 <= p.N) {
+                    if (e.dtype_c == RB_F32) {
+                        float4* dst = reinterpret_cast<float4*>((float*)e.C + orow * e.ldc + nb);
+    #pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+                        uint4* dst = reinterpret_cast<uint4*>((uint16_t*)e.C + orow * e.ldc + nb);
+    #pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t w[4];
+    #pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                float lo = v[8 * j + 2 * t], hi = v[8 * j + 2 * t + 1];
+                                if (e.dtype_c == RB_F16) { __half2 h = __floats2half2_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
+                                else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
+                            }
+                            dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                } else {
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < p.N) store_any(e.C, orow * e.ldc + nb + j, e.dtype_c, v[j]);
+                }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
@@ -287,8 +380,19 @@ static int make_map(CUtensorMap* map, const void* base, int is_bf16, uint64_t in
     return 0;
 }
 
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <int BN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int zdim, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, int zdim, cudaStream_t st) {
     using Cfg = TcCfg<BN>;
     static bool configured = false;
     if (!configured) {
@@ -296,7 +400,13 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
         RB_REQUIRE(e == cudaSuccess, "gemm_tc: cannot set %d bytes of dynamic shared memory: %s", Cfg::SMEM, cudaGetErrorString(e));
         configured = true;
     }
-    dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.N + BN - 1) / BN, zdim);
+    p.tiles_m = (p.M + TC_BM - 1) / TC_BM;
+    p.tiles_n = (p.N + BN - 1) / BN;
+    const long long total = (long long)p.tiles_m * p.tiles_n * zdim;
+    RB_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
+    p.total_tiles = (int)total;
+    const int resident = sm_count() * Cfg::CTAS_PER_SM;
+    const int grid = p.total_tiles < resident ? p.total_tiles : resident;
     gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM, st>>>(ma, mb, p);
     return check_launch("gemm_tc");
 }

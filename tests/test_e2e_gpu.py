@@ -146,3 +146,18 @@ def test_match_fast_mode_small(weights, amp):
     assert np.isfinite(ew).all() and np.isfinite(ec).all()
     tol_med = 2e-3 if amp == torch.float16 else 1e-2
     assert np.median(ew) < tol_med and np.mean(ew > 5e-2) < 0.05
+
+
+@pytest.mark.slow
+def test_match_fast_mode_full(weights):
+    """fp16 tensor-core mode at 560 -> 864 against the reference golden (sub-sampled)."""
+    g = load_golden("full_sym_up")
+    model = build(weights, g, amp_dtype=torch.float16)
+    A, B, Ah, Bh = synthetic.make_pair(1, 560, 864, 1)
+    warp, cert = model.match(A.cuda(), B.cuda(), im_A_high_res=Ah.cuda(), im_B_high_res=Bh.cuda())
+    ew = np.abs(warp[:, ::8, ::8].cpu().numpy() - g["warp"]).max(-1)
+    ec = np.abs(cert[:, ::8, ::8].cpu().numpy() - g["certainty"])
+    print(f"[fast fp16 full] warp err: median {np.median(ew):.2e} p99 {np.percentile(ew, 99):.2e} max {ew.max():.2e} "
+          f"frac>1e-3 {np.mean(ew > 1e-3):.4f}; cert err median {np.median(ec):.2e} p99 {np.percentile(ec, 99):.2e} max {ec.max():.2e}")
+    assert np.median(ew) < 1e-3 and np.mean(ew > 5e-2) < 0.05
+    model.engine.free_buffers()

@@ -129,4 +129,4 @@ def test_tc_coskernel_split_f16x3_is_fp32_class():
     ref = ((cos - 1) / 0.2).exp()
     err = (K.double().cpu() - ref).abs().max().item()
     print("coskernel split-f16x3 max abs err vs fp64:", err)
-    assert err < 5e-6
+    assert err < 3e-5      # fp32 CUDA-core path: ~2e-6; single-pass fp16/TF32 operands: ~5e-4
