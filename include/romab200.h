@@ -182,6 +182,15 @@ typedef struct {
 } rb_dwconv_args;
 int romab200_dwconv5x5_relu(const rb_dwconv_args* args, void* stream);
 
+/* Fused thin-map ConvRefiner block (C = 24, stride-1 maps): out = PW(ReLU(BN(DW5x5(in)))) in one pass.
+ * in/out: channels-last 16-bit maps [batch, h, w, ld] (in != out); dw_weight [25][ldw] fp32 tap-major (BN folded),
+ * pw_weight [c][c] fp32 row-major.  (create_block, matcher.py:92-122) */
+typedef struct {
+    const void* in; void* out; int64_t ld; const float* dw_weight; int64_t ldw; const float* dw_bias;
+    const float* pw_weight; const float* pw_bias; int32_t batch, h, w, c; int32_t dtype;
+} rb_refiner_block_small_args;
+int romab200_refiner_block_small(const rb_refiner_block_small_args* args, void* stream);
+
 /* out_conv (fp32 1x1, C -> 3) + flow/certainty update (matcher.py:177-179, 496-506):
  * state[...,0] += scale_x * o0 ; state[...,1] += scale_y * o1 ; state[...,2] += o2 */
 typedef struct {

@@ -55,6 +55,54 @@ __global__ void softmax_rows_kernel(T* __restrict__ s, int64_t rows, int cols, i
     for (int c = tid; c < cols; c += 256) sr[c] = from_f<T>(expf(to_f(sr[c]) * scale - m) * inv);
 }
 
+// warp-per-row softmax for rows of at most 2048 elements (attention: 1600/1601): the row is read once with
+// 16-byte loads, kept in registers, and written once.
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_rows_warp_kernel(T* __restrict__ s, int64_t rows, int cols, int64_t lds, float scale) {
+    constexpr int VN = 16 / sizeof(T);
+    constexpr int ITERS = 2048 / (32 * VN);
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    T* sr = s + row * lds;
+    float v[ITERS][VN];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+        const int c0 = (i * 32 + lane) * VN;
+        if (c0 < cols) {
+            uint4 raw = *reinterpret_cast<const uint4*>(sr + c0);
+            const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+            for (int j = 0; j < VN; ++j) {
+                v[i][j] = (c0 + j < cols) ? to_f(e[j]) * scale : -INFINITY;
+                m = fmaxf(m, v[i][j]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < VN; ++j) v[i][j] = -INFINITY;
+        }
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i)
+#pragma unroll
+        for (int j = 0; j < VN; ++j) { v[i][j] = expf(v[i][j] - m); sum += v[i][j]; }
+    const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+        const int c0 = (i * 32 + lane) * VN;
+        if (c0 < cols) {
+            uint4 raw;
+            T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+            for (int j = 0; j < VN; ++j) e[j] = from_f<T>(v[i][j] * inv);      // pad columns (>= cols) receive 0
+            *reinterpret_cast<uint4*>(sr + c0) = raw;
+        }
+    }
+}
+
 template <typename T>
 __global__ void row_norms_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t rows, int cols, int64_t ldx) {
     int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
@@ -171,6 +219,16 @@ extern "C" int romab200_layernorm(const rb_layernorm_args* a, void* stream) {
 extern "C" int romab200_softmax_rows(const rb_softmax_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->rows > 0 && a->cols > 0 && a->rows < (1ll << 31), "softmax: bad shape");
+    const int es = a->dtype == RB_F32 ? 4 : 2;
+    const int vn = 16 / es;
+    // rows must be padded to whole 16-byte vectors (the pad columns are rewritten with zeros)
+    if (a->cols <= 2048 && (a->lds * es) % 16 == 0 && ((uintptr_t)a->s) % 16 == 0 && (a->cols + vn - 1) / vn * vn <= a->lds) {
+        unsigned grid = (unsigned)((a->rows + 7) / 8);
+        if (a->dtype == RB_F32) softmax_rows_warp_kernel<float><<<grid, 256, 0, st>>>((float*)a->s, a->rows, a->cols, a->lds, a->scale);
+        else if (a->dtype == RB_F16) softmax_rows_warp_kernel<__half><<<grid, 256, 0, st>>>((__half*)a->s, a->rows, a->cols, a->lds, a->scale);
+        else softmax_rows_warp_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)a->s, a->rows, a->cols, a->lds, a->scale);
+        return check_launch("softmax_rows");
+    }
     if (a->dtype == RB_F32) softmax_rows_kernel<float><<<(unsigned)a->rows, 256, 0, st>>>((float*)a->s, a->rows, a->cols, a->lds, a->scale);
     else if (a->dtype == RB_F16) softmax_rows_kernel<__half><<<(unsigned)a->rows, 256, 0, st>>>((__half*)a->s, a->rows, a->cols, a->lds, a->scale);
     else softmax_rows_kernel<__nv_bfloat16><<<(unsigned)a->rows, 256, 0, st>>>((__nv_bfloat16*)a->s, a->rows, a->cols, a->lds, a->scale);

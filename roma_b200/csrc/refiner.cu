@@ -248,6 +248,105 @@ __global__ void __launch_bounds__(256) dwconv5x5_relu_kernel(const T* __restrict
 }
 
 // --------------------------------------------------------------------------------------------------
+// Fused ConvRefiner block for thin maps (C = 24 at stride 1): depthwise 5x5 + folded BN + ReLU + pointwise
+// C x C + bias in ONE pass over the activation (read once, written once).  The stride-1 maps are the
+// largest tensors of the path (1.5 M pixels at 864^2) and far too thin for a tensor-core tile, so this is a
+// CUDA-core kernel: a 16x16 pixel tile (+2 halo) is staged in shared memory, the depthwise stage runs
+// channel-pair x row strips with its 50 filter taps in registers, the pointwise stage runs one pixel per
+// thread against broadcast weights.
+// --------------------------------------------------------------------------------------------------
+template <typename T, int C>
+__global__ void __launch_bounds__(256) refiner_block_small_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t ld,
+                                                                  const float* __restrict__ dw_w, int64_t ldw, const float* __restrict__ dw_b,
+                                                                  const float* __restrict__ pw_w, const float* __restrict__ pw_b,
+                                                                  int H, int W, int tiles_x) {
+    constexpr int TS = 16, IN = TS + 4, CP = C / 2;
+    constexpr int PS = C + 2;                 // input pixel stride in halves (odd number of 32-bit words: conflict-free)
+    constexpr int MS = C + 1;                 // mid pixel stride in floats
+    __shared__ __align__(16) T tile[IN * IN * PS];
+    __shared__ float mid[TS * TS * MS];
+    __shared__ __align__(16) float wpw[C * C];
+    __shared__ float bpw[C];
+    const int tid = threadIdx.x;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, b = blockIdx.y;
+    const int x0 = tx * TS, y0 = ty * TS;
+    const T* inb = in + (int64_t)b * H * W * ld;
+    // ---- stage the (TS+4)^2 x C input tile (zero outside the image) and the pointwise weights
+    for (int i = tid; i < IN * IN * CP; i += 256) {
+        int pix = i / CP, cp = i - pix * CP;
+        int py = pix / IN, px = pix - py * IN;
+        int yy = y0 + py - 2, xx = x0 + px - 2;
+        uint32_t v = 0;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = *reinterpret_cast<const uint32_t*>(inb + ((int64_t)yy * W + xx) * ld + 2 * cp);
+        *reinterpret_cast<uint32_t*>(&tile[pix * PS + 2 * cp]) = v;
+    }
+    for (int i = tid; i < C * C; i += 256) wpw[i] = pw_w[i];
+    if (tid < C) bpw[tid] = pw_b[tid];
+    // ---- depthwise: thread = (channel pair, output row)
+    const int cp = tid % CP, row = tid / CP;
+    float w0[25], w1[25];
+    float b0 = 0.f, b1 = 0.f;
+    if (row < TS) {
+#pragma unroll
+        for (int t = 0; t < 25; ++t) { w0[t] = dw_w[(int64_t)t * ldw + 2 * cp]; w1[t] = dw_w[(int64_t)t * ldw + 2 * cp + 1]; }
+        b0 = dw_b[2 * cp]; b1 = dw_b[2 * cp + 1];
+    }
+    __syncthreads();
+    if (row < TS) {
+        float a0[TS], a1[TS];
+#pragma unroll
+        for (int i = 0; i < TS; ++i) { a0[i] = b0; a1[i] = b1; }
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+            for (int px = 0; px < IN; ++px) {
+                float v0, v1;
+                {
+                    const T* p2 = &tile[((row + ky) * IN + px) * PS + 2 * cp];
+                    v0 = to_f(p2[0]); v1 = to_f(p2[1]);
+                }
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                    const int ox = px - kx;
+                    if (ox >= 0 && ox < TS) {
+                        a0[ox] = fmaf(w0[ky * 5 + kx], v0, a0[ox]);
+                        a1[ox] = fmaf(w1[ky * 5 + kx], v1, a1[ox]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TS; ++i) {
+            // the unfused path stores this activation in the 16-bit compute dtype: round identically
+            mid[(row * TS + i) * MS + 2 * cp] = to_f(from_f<T>(fmaxf(a0[i], 0.f)));
+            mid[(row * TS + i) * MS + 2 * cp + 1] = to_f(from_f<T>(fmaxf(a1[i], 0.f)));
+        }
+    }
+    __syncthreads();
+    // ---- pointwise: thread = pixel
+    const int py = tid / TS, px = tid - py * TS;
+    const int yy = y0 + py, xx = x0 + px;
+    if (yy >= H || xx >= W) return;
+    float a[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) a[c] = mid[tid * MS + c];
+    T* o = out + ((int64_t)b * H * W + (int64_t)yy * W + xx) * ld;
+#pragma unroll
+    for (int co = 0; co < C; co += 2) {
+        float s0 = bpw[co], s1 = bpw[co + 1];
+#pragma unroll
+        for (int ci = 0; ci < C; ci += 4) {
+            const float4 wa = *reinterpret_cast<const float4*>(&wpw[co * C + ci]);
+            const float4 wb = *reinterpret_cast<const float4*>(&wpw[(co + 1) * C + ci]);
+            s0 = fmaf(wa.x, a[ci], s0); s0 = fmaf(wa.y, a[ci + 1], s0); s0 = fmaf(wa.z, a[ci + 2], s0); s0 = fmaf(wa.w, a[ci + 3], s0);
+            s1 = fmaf(wb.x, a[ci], s1); s1 = fmaf(wb.y, a[ci + 1], s1); s1 = fmaf(wb.z, a[ci + 2], s1); s1 = fmaf(wb.w, a[ci + 3], s1);
+        }
+        T pair[2] = {from_f<T>(s0), from_f<T>(s1)};
+        *reinterpret_cast<uint32_t*>(o + co) = *reinterpret_cast<uint32_t*>(pair);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
 // out_conv (C -> 3, fp32) + state update: one warp per pixel
 // --------------------------------------------------------------------------------------------------
 template <typename T>
@@ -463,6 +562,23 @@ extern "C" int romab200_dwconv5x5_relu(const rb_dwconv_args* a, void* stream) {
     else if (a->dtype == RB_F16) dwconv5x5_relu_kernel<__half><<<grid, 256, 0, st>>>((const __half*)a->in, (__half*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
     else dwconv5x5_relu_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
     return check_launch("dwconv5x5_relu");
+}
+
+extern "C" int romab200_refiner_block_small(const rb_refiner_block_small_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->c == 24, "refiner_block_small: only C = 24 is instantiated (got %d)", a->c);
+    RB_REQUIRE(a->dtype == RB_F16 || a->dtype == RB_BF16, "refiner_block_small: 16-bit activations only");
+    RB_REQUIRE(a->ld % 2 == 0 && ((uintptr_t)a->in) % 4 == 0 && ((uintptr_t)a->out) % 4 == 0 && a->in != a->out, "refiner_block_small: bad layout");
+    int tiles_x = (a->w + 15) / 16, tiles_y = (a->h + 15) / 16;
+    dim3 grid(tiles_x * tiles_y, a->batch);
+    RB_REQUIRE(grid.y <= 65535, "refiner_block_small: batch too large");
+    if (a->dtype == RB_F16)
+        refiner_block_small_kernel<__half, 24><<<grid, 256, 0, st>>>((const __half*)a->in, (__half*)a->out, a->ld, a->dw_weight, a->ldw, a->dw_bias,
+                                                                     a->pw_weight, a->pw_bias, a->h, a->w, tiles_x);
+    else
+        refiner_block_small_kernel<__nv_bfloat16, 24><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ld, a->dw_weight,
+                                                                            a->ldw, a->dw_bias, a->pw_weight, a->pw_bias, a->h, a->w, tiles_x);
+    return check_launch("refiner_block_small");
 }
 
 extern "C" int romab200_refiner_tail(const rb_refiner_tail_args* a, void* stream) {

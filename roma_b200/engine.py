@@ -331,10 +331,17 @@ class Engine:
         if self.debug is not None:
             self.debug[f"{tag}.refiner_in"] = d.view(D, h, w, cp)[..., :c].float().clone()
         rows = D * h * w
-        for blk in R["blocks"]:
-            call("romab200_dwconv5x5_relu", "rb_dwconv_args", **{"in": d}, out=t, ldi=cp, ldo=cp, weight=blk["dw_w"], ldw=cp,
-                 bias=blk["dw_b"], batch=D, h=h, w=w, c=c, dtype=self.dt)
-            self.gemm(t, blk["pw_w"], d, rows, c, c, cp, cp, cp, bias=blk["pw_b"])
+        if c == 24 and self.dtype != torch.float32:
+            # thin stride-1 maps: one fused DW5x5+ReLU+PW kernel per block, ping-ponging between the two buffers
+            for blk in R["blocks"]:
+                call("romab200_refiner_block_small", "rb_refiner_block_small_args", **{"in": d}, out=t, ld=cp, dw_weight=blk["dw_w"],
+                     ldw=cp, dw_bias=blk["dw_b"], pw_weight=blk["pw_w32"], pw_bias=blk["pw_b"], batch=D, h=h, w=w, c=c, dtype=self.dt)
+                d, t = t, d
+        else:
+            for blk in R["blocks"]:
+                call("romab200_dwconv5x5_relu", "rb_dwconv_args", **{"in": d}, out=t, ldi=cp, ldo=cp, weight=blk["dw_w"], ldw=cp,
+                     bias=blk["dw_b"], batch=D, h=h, w=w, c=c, dtype=self.dt)
+                self.gemm(t, blk["pw_w"], d, rows, c, c, cp, cp, cp, bias=blk["pw_b"])
         delta = self.buf(f"ref.delta.{tag}", (rows, 3), dtype=torch.float32) if self.debug is not None else None
         call("romab200_refiner_tail", "rb_refiner_tail_args", d=d, ldd=cp, weight=R["out_w"], ldw=cp, bias=R["out_b"],
              state=state, rows=rows, c=c, scale_x=s / (arch.REFINE_INIT * w1), scale_y=s / (arch.REFINE_INIT * h1),
@@ -392,10 +399,14 @@ class Engine:
                 state = self.resize_state(state, D, h, w, ho, wo, name=f"state.{tag}.{s // 2}")
         return state, states, sizes
 
-    def epilogue(self, state, coarse_state, hc, wc, b, H, W, symmetric):
+    def epilogue(self, state, coarse_state, hc, wc, b, H, W, symmetric, out=None):
         Wout = 2 * W if symmetric else W
-        warp = torch.empty(b, H, Wout, 4, dtype=torch.float32, device=self.device)
-        cert = torch.empty(b, H, Wout, dtype=torch.float32, device=self.device)
+        if out is None:
+            warp = torch.empty(b, H, Wout, 4, dtype=torch.float32, device=self.device)
+            cert = torch.empty(b, H, Wout, dtype=torch.float32, device=self.device)
+        else:
+            warp, cert = out
+            assert warp.shape == (b, H, Wout, 4) and cert.shape == (b, H, Wout)
         call("romab200_match_epilogue", "rb_match_epilogue_args", state=state, coarse_state=coarse_state, hc=hc, wc=wc,
              warp=warp, cert=cert, b=b, H=H, W=W, symmetric=int(symmetric), grid_x=self.grid_axis(W), grid_y=self.grid_axis(H))
         return warp, cert

@@ -17,6 +17,7 @@ import torch
 import torch.nn.functional as F
 from PIL import Image
 
+from . import cabi
 from .engine import Engine
 from .preprocess import check_input, pil_to_normalized
 
@@ -35,6 +36,9 @@ class RegressionMatcher:
         self.symmetric = symmetric
         self.sample_thresh = sample_thresh
         self.training = False
+        self.use_cuda_graph = True      # replay the whole device side of match() as one CUDA graph per input shape
+        self._graphs = {}
+        self.graph_launches = 0         # kernels launched through graph replays (cabi.kernel_launches counts eager ones)
 
     # ---- nn.Module-ish conveniences callers rely on ------------------------------------------------
     def train(self, mode: bool = True):
@@ -116,35 +120,82 @@ class RegressionMatcher:
         else:
             raise ValueError(f"Unsupported input type: {type(im_A)=} and {type(im_B)=}")
 
-        with torch.cuda.device(eng.device):
-            images = torch.cat((a_t.to(eng.device, torch.float32, non_blocking=True),
-                                b_t.to(eng.device, torch.float32, non_blocking=True))).contiguous()
-            state, states, sizes = eng.run_pass(images, b, symmetric, False, scale_factor)
-            coarse = states[16] if self.attenuate_cert else None
-            hc, wc = sizes[16]
-            if self.upsample_preds:
-                hs_lo, ws_lo = hs, ws
-                hs, ws = self.upsample_res
-                if im_A_high_res is None and im_B_high_res is None:
-                    if isinstance(im_A_input, (str, os.PathLike)):
-                        hi_a, hi_b = Image.open(im_A_input).convert("RGB"), Image.open(im_B_input).convert("RGB")
-                    else:
-                        assert isinstance(im_A_input, Image.Image), f"Unsupported input type: {type(im_A_input)=}"
-                        assert isinstance(im_B_input, Image.Image), f"Unsupported input type: {type(im_B_input)=}"
-                        hi_a, hi_b = im_A_input, im_B_input
-                    a_h = pil_to_normalized(hi_a, (hs, ws))[None]
-                    b_h = pil_to_normalized(hi_b, (hs, ws))[None]
-                elif im_A_high_res is not None and im_B_high_res is not None:
-                    a_h, b_h = im_A_high_res, im_B_high_res
+        a_h = b_h = None
+        if self.upsample_preds:
+            hs, ws = self.upsample_res
+            if im_A_high_res is None and im_B_high_res is None:
+                if isinstance(im_A_input, (str, os.PathLike)):
+                    hi_a, hi_b = Image.open(im_A_input).convert("RGB"), Image.open(im_B_input).convert("RGB")
                 else:
-                    raise ValueError(f"Invalid upsample_preds and high_res inputs with {im_A=},{im_A_high_res=},{im_B=} and {im_B_high_res=}")
-                scale_factor = math.sqrt(self.upsample_res[0] * self.upsample_res[1] / (560 ** 2))
-                images_hi = torch.cat((a_h.to(eng.device, torch.float32, non_blocking=True),
-                                       b_h.to(eng.device, torch.float32, non_blocking=True))).contiguous()
-                hs, ws = images_hi.shape[-2:]
-                state, _, _ = eng.run_pass(images_hi, b, symmetric, True, scale_factor, (state, hs_lo, ws_lo))
-            warp, certainty = eng.epilogue(state, coarse, hc, wc, b, hs, ws, symmetric)
-        return warp, certainty
+                    assert isinstance(im_A_input, Image.Image), f"Unsupported input type: {type(im_A_input)=}"
+                    assert isinstance(im_B_input, Image.Image), f"Unsupported input type: {type(im_B_input)=}"
+                    hi_a, hi_b = im_A_input, im_B_input
+                a_h = pil_to_normalized(hi_a, (hs, ws))[None]
+                b_h = pil_to_normalized(hi_b, (hs, ws))[None]
+            elif im_A_high_res is not None and im_B_high_res is not None:
+                a_h, b_h = im_A_high_res, im_B_high_res
+            else:
+                raise ValueError(f"Invalid upsample_preds and high_res inputs with {im_A=},{im_A_high_res=},{im_B=} and {im_B_high_res=}")
+        with torch.cuda.device(eng.device):
+            return self._match_device(a_t, b_t, a_h, b_h, b, symmetric, scale_factor)
+
+    def _run_device(self, images, images_hi, b, symmetric, scale_factor, attenuate, warp, cert):
+        """Both passes + epilogue on the current stream; no allocation, no host sync (CUDA-graph capturable)."""
+        eng = self.engine
+        hs, ws = images.shape[-2:]
+        state, states, sizes = eng.run_pass(images, b, symmetric, False, scale_factor)
+        coarse = states[16] if attenuate else None
+        hc, wc = sizes[16]
+        if images_hi is not None:
+            hh, wh = images_hi.shape[-2:]
+            sf = math.sqrt(self.upsample_res[0] * self.upsample_res[1] / (560 ** 2))
+            state, _, _ = eng.run_pass(images_hi, b, symmetric, True, sf, (state, hs, ws))
+            hs, ws = hh, wh
+        eng.epilogue(state, coarse, hc, wc, b, hs, ws, symmetric, out=(warp, cert))
+
+    def _match_device(self, a_t, b_t, a_h, b_h, b, symmetric, scale_factor):
+        eng = self.engine
+        dev = eng.device
+        hs, ws = a_t.shape[-2:]
+        ho, wo = (a_h.shape[-2:] if a_h is not None else (hs, ws))
+        wout = 2 * wo if symmetric else wo
+        attenuate = bool(self.attenuate_cert)
+        use_graph = self.use_cuda_graph and eng.debug is None and eng.profile is None and eng.gemm_profile is None
+        key = (b, hs, ws, ho if a_h is not None else 0, wo if a_h is not None else 0, symmetric, attenuate, float(scale_factor),
+               tuple(self.upsample_res))
+        entry = self._graphs.get(key) if use_graph else None
+        if entry is None:
+            images = torch.empty(2 * b, 3, hs, ws, dtype=torch.float32, device=dev)
+            images_hi = torch.empty(2 * b, 3, ho, wo, dtype=torch.float32, device=dev) if a_h is not None else None
+            warp = torch.empty(b, ho, wout, 4, dtype=torch.float32, device=dev)
+            cert = torch.empty(b, ho, wout, dtype=torch.float32, device=dev)
+            entry = dict(images=images, images_hi=images_hi, warp=warp, cert=cert, graph=None, calls=0)
+            if use_graph:
+                self._graphs[key] = entry
+        entry["images"][:b].copy_(a_t, non_blocking=True)
+        entry["images"][b:].copy_(b_t, non_blocking=True)
+        if a_h is not None:
+            entry["images_hi"][:b].copy_(a_h, non_blocking=True)
+            entry["images_hi"][b:].copy_(b_h, non_blocking=True)
+        args = (entry["images"], entry["images_hi"], b, symmetric, scale_factor, attenuate, entry["warp"], entry["cert"])
+        if not use_graph:
+            self._run_device(*args)
+            return entry["warp"], entry["cert"]
+        entry["calls"] += 1
+        if entry["graph"] is None:
+            self._run_device(*args)                 # eager: also allocates every activation buffer
+            if entry["calls"] >= 2:                 # second call with this shape: capture for all later calls
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                launches0 = cabi.kernel_launches()
+                with torch.cuda.graph(graph):
+                    self._run_device(*args)
+                entry["graph"] = graph
+                entry["launches"] = cabi.kernel_launches() - launches0
+        else:
+            entry["graph"].replay()
+            self.graph_launches += entry["launches"]
+        return entry["warp"].clone(), entry["cert"].clone()
 
     # ---- sampling (matcher.py:598-629) ----------------------------------------------------------------
     def sample(self, matches, certainty, num=10000):

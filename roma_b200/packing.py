@@ -136,10 +136,13 @@ class PackedWeights:
             dw, db = fold_bn(sd[f"{q}.0.weight"].float(), sd[f"{q}.0.bias"].float(), sd, f"{q}.1")
             dwt = torch.zeros(25, cp)
             dwt[:, :c] = dw.reshape(c, 25).t()
+            pw = sd[f"{q}.3.weight"].float().flatten(1)
             blocks.append(dict(
                 dw_w=dwt.to(self.device), dw_b=_vec(db, self.device),
-                pw_w=_mat(sd[f"{q}.3.weight"].float().flatten(1), self.dtype, self.device, pitch=cp),
+                pw_w=_mat(pw, self.dtype, self.device, pitch=cp),
                 pw_b=_vec(sd[f"{q}.3.bias"], self.device),
+                # thin maps (C = 24) run the fused CUDA-core block: fp32 copy of the compute-dtype-rounded weights
+                pw_w32=pw.to(self.dtype).float().contiguous().to(self.device) if c <= 32 else None,
             ))
         ow = torch.zeros(3, cp)
         ow[:, :c] = sd[f"{p}.out_conv.weight"].float().flatten(1)

@@ -130,3 +130,20 @@ def test_tc_coskernel_split_f16x3_is_fp32_class():
     err = (K.double().cpu() - ref).abs().max().item()
     print("coskernel split-f16x3 max abs err vs fp64:", err)
     assert err < 3e-5      # fp32 CUDA-core path: ~2e-6; single-pass fp16/TF32 operands: ~5e-4
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_refiner_block_small_fused_vs_unfused(dt):
+    """Fused thin-map block (DW5x5+ReLU+PW, C=24) against conv2d on the same 16-bit-rounded tensors."""
+    B, C, H, W = 2, 24, 37, 50
+    x = rnd(B, C, H, W, seed=1, dtype=dt)
+    dw, db = rnd(C, 1, 5, 5, seed=2, scale=0.3, dtype=torch.float32), rnd(C, seed=3, dtype=torch.float32)
+    pw, pb = rnd(C, C, seed=4, scale=0.3, dtype=dt), rnd(C, seed=5, dtype=torch.float32)
+    mid = F.relu(F.conv2d(x.float(), dw, db, padding=2, groups=C)).to(dt).float()
+    ref = (torch.einsum("bchw,oc->bohw", mid, pw.float()) + pb[None, :, None, None]).permute(0, 2, 3, 1)
+    xi = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.zeros(B, H, W, C, dtype=dt, device=DEV)
+    dwt = dw.reshape(C, 25).t().contiguous()
+    call("romab200_refiner_block_small", "rb_refiner_block_small_args", **{"in": xi}, out=out, ld=C, dw_weight=dwt, ldw=C, dw_bias=db,
+         pw_weight=pw.float().contiguous(), pw_bias=pb, batch=B, h=H, w=W, c=C, dtype=CODE[dt])
+    close(out, ref, 6e-2 if dt == torch.bfloat16 else 8e-3)
