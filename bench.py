@@ -228,9 +228,13 @@ def run_ours(args):
     if rank == 0:
         peaks = load_peaks()
         by = {}
-        for backend, flops, s, e in gemm_prof:
+        shapes = {}
+        for backend, flops, s, e, shape in gemm_prof:
+            t = s.elapsed_time(e)
             d = by.setdefault(backend, [0.0, 0.0, 0])
-            d[0] += flops; d[1] += s.elapsed_time(e); d[2] += 1
+            d[0] += flops; d[1] += t; d[2] += 1
+            sh = shapes.setdefault((backend,) + shape, [0.0, 0.0, 0])
+            sh[0] += flops; sh[1] += t; sh[2] += 1
         dom = max(by, key=lambda k: by[k][1]) if by else None
         roofline = None
         if dom:
@@ -270,6 +274,9 @@ def run_ours(args):
             "gemm_backends": {k: {"tflops": v[0] / (v[1] / 1e3) / 1e12, "ms_per_step": v[1] / args.steps, "launches_per_step": v[2] / args.steps}
                               for k, v in by.items()},
             "whole_path_tflops": FLOP_PER_PAIR * pairs / (total_ms / 1e3) / 1e12,
+            "top_gemm_shapes": [{"backend": k[0], "MxNxK,batch": list(k[1:]), "ms_per_step": round(v[1] / args.steps, 3),
+                                 "launches_per_step": v[2] / args.steps, "tflops": round(v[0] / (v[1] / 1e3) / 1e12, 1)}
+                                for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:16]],
         }
         print(json.dumps(line))
     if world > 1:

@@ -190,6 +190,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
     if (e.R) e.R = (const char*)e.R + (z0 * p.sr0 + z1 * p.sr1) * dtype_size(e.dtype_r);
     if (e.norm_a) e.norm_a += z0 * p.sna0;
     if (e.norm_b) e.norm_b += z0 * p.snb0;
+    // fast path (GP trailing updates, plain fp32 linears): whole float4 groups, branches hoisted out of the element loop
+    const bool fast = e.epi == RB_EPI_LINEAR && e.rowmap == RB_ROWMAP_NONE && e.dtype_c == RB_F32 && (e.ldc & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(e.C) & 15) == 0 && (!e.R || (e.dtype_r == RB_F32 && (e.ldr & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(e.R) & 15) == 0)) && e.act == RB_ACT_NONE && !e.col_scale;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
         int m = m0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
@@ -197,10 +201,19 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
         int64_t orow = e.map_row(m);
         if (orow < 0) continue;
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-            int n = n0 + (j < 4 ? tx * 4 + j : BN / 2 + tx * 4 + (j - 4));
+        for (int jg = 0; jg < TN; jg += 4) {
+            const int n = n0 + (jg < 4 ? tx * 4 : BN / 2 + tx * 4);
             if (n >= p.N) continue;
-            store_any(e.C, orow * e.ldc + n, e.dtype_c, e.apply(acc[i][j], m, n, orow));
+            if (fast && n + 3 < p.N) {
+                float4 v = make_float4(e.alpha * acc[i][jg], e.alpha * acc[i][jg + 1], e.alpha * acc[i][jg + 2], e.alpha * acc[i][jg + 3]);
+                if (e.bias) { const float4 bb = *reinterpret_cast<const float4*>(e.bias + n); v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w; }
+                if (e.R) { const float4 r = *reinterpret_cast<const float4*>((const float*)e.R + orow * e.ldr + n); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+                *reinterpret_cast<float4*>((float*)e.C + orow * e.ldc + n) = v;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < p.N) store_any(e.C, orow * e.ldc + n + j, e.dtype_c, e.apply(acc[i][jg + j], m, n + j, orow));
+            }
         }
     }
 }

@@ -121,7 +121,63 @@ struct PrologueParams {
     int D, h, w, cf, emb;
     const float* emb_w; const float* emb_b; float disp_scale;
     const float* gx; const float* gy; const float* winx; const float* winy;
+    int vec_ok;
 };
+
+// thin maps (stride 1: 9 feature channels, 24 in total): one THREAD per pixel, the whole d row is assembled in
+// registers and written with 16-byte stores (a warp per pixel would leave 3/4 of the lanes idle on 1.5 M pixels)
+template <typename T>
+__global__ void __launch_bounds__(256) refiner_prologue_small_kernel(const PrologueParams p) {
+    constexpr int MAXC = 32;
+    const int64_t pix = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t hw = (int64_t)p.h * p.w;
+    if (pix >= p.D * hw) return;
+    const int item = (int)(pix / hw);
+    const int rem = (int)(pix - item * hw);
+    const int y = rem / p.w, x = rem - y * p.w;
+    const float fx = p.state[pix * 3 + 0], fy = p.state[pix * 3 + 1];
+    const T* feat = (const T*)p.feat;
+    const T* xrow = feat + ((int64_t)item * hw + rem) * p.ldf;
+    const T* yimg = feat + (int64_t)((item + p.y_shift) % p.n_img) * hw * p.ldf;
+    const int cf = p.cf;
+    const float ix = ((fx + 1.f) * p.w - 1.f) * 0.5f, iy = ((fy + 1.f) * p.h - 1.f) * 0.5f;
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const float wx1 = ix - x0f, wx0 = (x0f + 1.f) - ix, wy1 = iy - y0f, wy0 = (y0f + 1.f) - iy;
+    const bool vx0 = x0 >= 0 && x0 < p.w, vx1 = x0 + 1 >= 0 && x0 + 1 < p.w;
+    const bool vy0 = y0 >= 0 && y0 < p.h, vy1 = y0 + 1 >= 0 && y0 + 1 < p.h;
+    const T* p00 = yimg + ((int64_t)y0 * p.w + x0) * p.ldf;
+    const T* p01 = p00 + p.ldf;
+    const T* p10 = p00 + (int64_t)p.w * p.ldf;
+    const T* p11 = p10 + p.ldf;
+    T row[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) row[c] = from_f<T>(0.f);
+    for (int c = 0; c < cf; ++c) {
+        float v = 0.f;
+        if (vy0 && vx0) v += to_f(p00[c]) * (wx0 * wy0);
+        if (vy0 && vx1) v += to_f(p01[c]) * (wx1 * wy0);
+        if (vy1 && vx0) v += to_f(p10[c]) * (wx0 * wy1);
+        if (vy1 && vx1) v += to_f(p11[c]) * (wx1 * wy1);
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {          // static indexing keeps `row` in registers
+            if (k == c) row[k] = xrow[c];
+            if (k == cf + c) row[k] = from_f<T>(v);
+        }
+    }
+    const float ddx = p.disp_scale * (fx - p.gx[x]), ddy = p.disp_scale * (fy - p.gy[y]);
+    for (int e = 0; e < p.emb; ++e) {
+        const T v = from_f<T>(p.emb_w[2 * e] * ddx + p.emb_w[2 * e + 1] * ddy + p.emb_b[e]);
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k)
+            if (k == 2 * cf + e) row[k] = v;
+    }
+    T* drow = (T*)p.d + pix * p.ldd;
+    constexpr int VN = Vec16<T>::N;
+#pragma unroll
+    for (int k = 0; k < MAXC; k += VN)
+        if (k < p.ldd) *reinterpret_cast<uint4*>(drow + k) = *reinterpret_cast<uint4*>(&row[k]);
+}
 
 template <typename T, int R>
 __global__ void __launch_bounds__(128) refiner_prologue_kernel(const PrologueParams p) {
@@ -152,14 +208,42 @@ __global__ void __launch_bounds__(128) refiner_prologue_kernel(const ProloguePar
     const T* p01 = p00 + p.ldf;
     const T* p10 = p00 + (int64_t)p.w * p.ldf;
     const T* p11 = p10 + p.ldf;
-    for (int c = lane; c < cf; c += 32) {
-        drow[c] = xrow[c];
-        float v = 0.f;
-        if (vy0 && vx0) v += to_f(p00[c]) * (wx0 * wy0);
-        if (vy0 && vx1) v += to_f(p01[c]) * (wx1 * wy0);
-        if (vy1 && vx0) v += to_f(p10[c]) * (wx0 * wy1);
-        if (vy1 && vx1) v += to_f(p11[c]) * (wx1 * wy1);
-        drow[cf + c] = from_f<T>(v);
+    constexpr int VN = Vec16<T>::N;
+    if (cf % VN == 0 && p.vec_ok) {
+        // 16-byte channel vectors: copy x, blend the four bilinear corners of y in fp32
+        const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
+        for (int c = lane * VN; c < cf; c += 32 * VN) {
+            *reinterpret_cast<uint4*>(drow + c) = *reinterpret_cast<const uint4*>(xrow + c);
+            float acc[VN], t[VN];
+#pragma unroll
+            for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+            if (vy0 && vx0) { load_vec<T>(p00 + c, t);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) acc[e] += t[e] * w00; }
+            if (vy0 && vx1) { load_vec<T>(p01 + c, t);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) acc[e] += t[e] * w01; }
+            if (vy1 && vx0) { load_vec<T>(p10 + c, t);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) acc[e] += t[e] * w10; }
+            if (vy1 && vx1) { load_vec<T>(p11 + c, t);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) acc[e] += t[e] * w11; }
+            T pk[VN];
+#pragma unroll
+            for (int e = 0; e < VN; ++e) pk[e] = from_f<T>(acc[e]);
+            *reinterpret_cast<uint4*>(drow + cf + c) = *reinterpret_cast<uint4*>(pk);
+        }
+    } else {
+        for (int c = lane; c < cf; c += 32) {
+            drow[c] = xrow[c];
+            float v = 0.f;
+            if (vy0 && vx0) v += to_f(p00[c]) * (wx0 * wy0);
+            if (vy0 && vx1) v += to_f(p01[c]) * (wx1 * wy0);
+            if (vy1 && vx0) v += to_f(p10[c]) * (wx0 * wy1);
+            if (vy1 && vx1) v += to_f(p11[c]) * (wx1 * wy1);
+            drow[cf + c] = from_f<T>(v);
+        }
     }
     // displacement embedding: 1x1 conv 2 -> emb on disp_scale * (flow - identity grid)   (matcher.py:135-148)
     const float ddx = p.disp_scale * (fx - p.gx[x]), ddy = p.disp_scale * (fy - p.gy[y]);
@@ -247,6 +331,82 @@ __global__ void __launch_bounds__(256) dwconv5x5_relu_kernel(const T* __restrict
         if (x0 + i < W) ob[(int64_t)(x0 + i) * ldo] = from_f<T>(fmaxf(acc[i], 0.f));
 }
 
+// 16-bit variant: lanes own channel PAIRS (one 32-bit shared-memory word = 2 channels), the tile is staged in the
+// storage dtype with 16-byte global loads, and the 2 x 25 filter taps live in registers.  Per 16x2 outputs a
+// thread issues 100 LDS.32 + 800 FFMA: the kernel is FP32-FMA bound (25 FMA per output element), not LDS bound.
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv5x5_relu_h2_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t ldi, int64_t ldo,
+                                                                const float* __restrict__ wgt, int64_t ldw, const float* __restrict__ bias,
+                                                                int H, int W, int C, int tiles_x) {
+    constexpr int TH = 8, TW = 16, CH = 64;
+    __shared__ __align__(16) T tile[(TH + 4) * (TW + 4) * CH];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int c0 = blockIdx.y * CH, b = blockIdx.z;
+    const int x0 = tx * TW, y0 = ty * TH;
+    const int cpad = (C + 7) & ~7;
+    const T* inb = in + (int64_t)b * H * W * ldi;
+    {   // all 8 global loads of a thread are issued before the first shared store (memory-level parallelism)
+        constexpr int NV = (TH + 4) * (TW + 4) * (CH / 8), PER = (NV + 255) / 256;
+        uint4 vals[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = threadIdx.x + k * 256;
+            const int pix = i >> 3, v = i & 7;
+            const int py = pix / (TW + 4), px = pix - py * (TW + 4);
+            const int yy = y0 + py - 2, xx = x0 + px - 2;
+            vals[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < NV && yy >= 0 && yy < H && xx >= 0 && xx < W && c0 + 8 * v < cpad)
+                vals[k] = *reinterpret_cast<const uint4*>(inb + ((int64_t)yy * W + xx) * ldi + c0 + 8 * v);
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = threadIdx.x + k * 256;
+            if (i < NV) *reinterpret_cast<uint4*>(&tile[(i >> 3) * CH + 8 * (i & 7)]) = vals[k];
+        }
+    }
+    const int c = c0 + 2 * lane;
+    const bool ok0 = c < C, ok1 = c + 1 < C;
+    float w0[25], w1[25];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) {
+        w0[t] = ok0 ? wgt[(int64_t)t * ldw + c] : 0.f;
+        w1[t] = ok1 ? wgt[(int64_t)t * ldw + c + 1] : 0.f;
+    }
+    const float b0 = ok0 ? bias[c] : 0.f, b1 = ok1 ? bias[c + 1] : 0.f;
+    __syncthreads();
+    float a0[TW], a1[TW];
+#pragma unroll
+    for (int i = 0; i < TW; ++i) { a0[i] = b0; a1[i] = b1; }
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+        for (int px = 0; px < TW + 4; ++px) {
+            T pr[2];
+            *reinterpret_cast<uint32_t*>(pr) = *reinterpret_cast<const uint32_t*>(&tile[((wid + ky) * (TW + 4) + px) * CH + 2 * lane]);
+            const float v0 = to_f(pr[0]), v1 = to_f(pr[1]);
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+                const int ox = px - kx;
+                if (ox >= 0 && ox < TW) {
+                    a0[ox] = fmaf(w0[ky * 5 + kx], v0, a0[ox]);
+                    a1[ox] = fmaf(w1[ky * 5 + kx], v1, a1[ox]);
+                }
+            }
+        }
+    }
+    const int yy = y0 + wid;
+    if (!ok0 || yy >= H) return;
+    T* ob = out + ((int64_t)b * H * W + (int64_t)yy * W) * ldo + c;
+#pragma unroll
+    for (int i = 0; i < TW; ++i) {
+        if (x0 + i < W) {
+            T pair[2] = {from_f<T>(fmaxf(a0[i], 0.f)), from_f<T>(ok1 ? fmaxf(a1[i], 0.f) : 0.f)};
+            *reinterpret_cast<uint32_t*>(ob + (int64_t)(x0 + i) * ldo) = *reinterpret_cast<uint32_t*>(pair);
+        }
+    }
+}
+
 // --------------------------------------------------------------------------------------------------
 // Fused ConvRefiner block for thin maps (C = 24 at stride 1): depthwise 5x5 + folded BN + ReLU + pointwise
 // C x C + bias in ONE pass over the activation (read once, written once).  The stride-1 maps are the
@@ -272,13 +432,28 @@ __global__ void __launch_bounds__(256) refiner_block_small_kernel(const T* __res
     const int x0 = tx * TS, y0 = ty * TS;
     const T* inb = in + (int64_t)b * H * W * ld;
     // ---- stage the (TS+4)^2 x C input tile (zero outside the image) and the pointwise weights
-    for (int i = tid; i < IN * IN * CP; i += 256) {
-        int pix = i / CP, cp = i - pix * CP;
-        int py = pix / IN, px = pix - py * IN;
-        int yy = y0 + py - 2, xx = x0 + px - 2;
-        uint32_t v = 0;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = *reinterpret_cast<const uint32_t*>(inb + ((int64_t)yy * W + xx) * ld + 2 * cp);
-        *reinterpret_cast<uint32_t*>(&tile[pix * PS + 2 * cp]) = v;
+    {   // 16-byte global loads, all issued before the first shared store
+        constexpr int VPP = C / 8, NV = IN * IN * VPP, PER = (NV + 255) / 256;
+        uint4 vals[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = tid + k * 256;
+            const int pix = i / VPP, v = i - pix * VPP;
+            const int py = pix / IN, px = pix - py * IN;
+            const int yy = y0 + py - 2, xx = x0 + px - 2;
+            vals[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < NV && yy >= 0 && yy < H && xx >= 0 && xx < W)
+                vals[k] = *reinterpret_cast<const uint4*>(inb + ((int64_t)yy * W + xx) * ld + 8 * v);
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = tid + k * 256;
+            if (i < NV) {
+                const int pix = i / VPP, v = i - pix * VPP;
+                uint32_t* dst = reinterpret_cast<uint32_t*>(&tile[pix * PS + 8 * v]);      // pixel stride 52 B: 4-byte aligned
+                dst[0] = vals[k].x; dst[1] = vals[k].y; dst[2] = vals[k].z; dst[3] = vals[k].w;
+            }
+        }
     }
     for (int i = tid; i < C * C; i += 256) wpw[i] = pw_w[i];
     if (tid < C) bpw[tid] = pw_b[tid];
@@ -300,11 +475,9 @@ __global__ void __launch_bounds__(256) refiner_block_small_kernel(const T* __res
         for (int ky = 0; ky < 5; ++ky) {
 #pragma unroll
             for (int px = 0; px < IN; ++px) {
-                float v0, v1;
-                {
-                    const T* p2 = &tile[((row + ky) * IN + px) * PS + 2 * cp];
-                    v0 = to_f(p2[0]); v1 = to_f(p2[1]);
-                }
+                T pr[2];
+                *reinterpret_cast<uint32_t*>(pr) = *reinterpret_cast<const uint32_t*>(&tile[((row + ky) * IN + px) * PS + 2 * cp]);
+                const float v0 = to_f(pr[0]), v1 = to_f(pr[1]);
 #pragma unroll
                 for (int kx = 0; kx < 5; ++kx) {
                     const int ox = px - kx;
@@ -512,7 +685,15 @@ extern "C" int romab200_refiner_prologue(const rb_refiner_prologue_args* a, void
     p.feat = a->feat; p.ldf = a->ldf; p.n_img = a->n_img; p.y_shift = a->y_shift; p.state = a->state; p.d = a->d; p.ldd = a->ldd;
     p.D = a->D; p.h = a->h; p.w = a->w; p.cf = a->cf; p.emb = a->emb; p.emb_w = a->emb_weight; p.emb_b = a->emb_bias;
     p.disp_scale = a->disp_scale; p.gx = a->grid_x; p.gy = a->grid_y; p.winx = a->win_x; p.winy = a->win_y;
+    const int es = a->dtype == RB_F32 ? 4 : 2;
+    p.vec_ok = (a->ldf * es) % 16 == 0 && (a->ldd * es) % 16 == 0 && ((uintptr_t)a->feat) % 16 == 0 && ((uintptr_t)a->d) % 16 == 0;
     int64_t pixels = (int64_t)a->D * a->h * a->w;
+    if (a->radius == 0 && 2 * a->cf + a->emb <= 32 && a->ldd <= 32 && p.vec_ok && a->dtype != RB_F32) {
+        unsigned g = (unsigned)((pixels + 255) / 256);
+        if (a->dtype == RB_F16) refiner_prologue_small_kernel<__half><<<g, 256, 0, st>>>(p);
+        else refiner_prologue_small_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(p);
+        return check_launch("refiner_prologue_small");
+    }
     unsigned grid = (unsigned)((pixels + 3) / 4);
 #define LAUNCH(T, R) refiner_prologue_kernel<T, R><<<grid, 128, 0, st>>>(p)
 #define BYR(T)                                                                                        \
@@ -558,6 +739,14 @@ extern "C" int romab200_dwconv5x5_relu(const rb_dwconv_args* a, void* stream) {
     int tiles_x = (a->w + 15) / 16, tiles_y = (a->h + 7) / 8;
     dim3 grid(tiles_x * tiles_y, (a->c + 31) / 32, a->batch);
     RB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "dwconv: grid too large");
+    const int cpad = (a->c + 7) & ~7;
+    if (a->dtype != RB_F32 && a->ldi % 8 == 0 && a->ldo % 2 == 0 && a->ldi >= cpad && a->ldo >= cpad &&
+        ((uintptr_t)a->in) % 16 == 0 && ((uintptr_t)a->out) % 4 == 0) {
+        dim3 grid2(tiles_x * tiles_y, (a->c + 63) / 64, a->batch);
+        if (a->dtype == RB_F16) dwconv5x5_relu_h2_kernel<__half><<<grid2, 256, 0, st>>>((const __half*)a->in, (__half*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
+        else dwconv5x5_relu_h2_kernel<__nv_bfloat16><<<grid2, 256, 0, st>>>((const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
+        return check_launch("dwconv5x5_relu");
+    }
     if (a->dtype == RB_F32) dwconv5x5_relu_kernel<float><<<grid, 256, 0, st>>>((const float*)a->in, (float*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
     else if (a->dtype == RB_F16) dwconv5x5_relu_kernel<__half><<<grid, 256, 0, st>>>((const __half*)a->in, (__half*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
     else dwconv5x5_relu_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
@@ -568,7 +757,7 @@ extern "C" int romab200_refiner_block_small(const rb_refiner_block_small_args* a
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->c == 24, "refiner_block_small: only C = 24 is instantiated (got %d)", a->c);
     RB_REQUIRE(a->dtype == RB_F16 || a->dtype == RB_BF16, "refiner_block_small: 16-bit activations only");
-    RB_REQUIRE(a->ld % 2 == 0 && ((uintptr_t)a->in) % 4 == 0 && ((uintptr_t)a->out) % 4 == 0 && a->in != a->out, "refiner_block_small: bad layout");
+    RB_REQUIRE(a->ld % 8 == 0 && ((uintptr_t)a->in) % 16 == 0 && ((uintptr_t)a->out) % 4 == 0 && a->in != a->out, "refiner_block_small: bad layout");
     int tiles_x = (a->w + 15) / 16, tiles_y = (a->h + 15) / 16;
     dim3 grid(tiles_x * tiles_y, a->batch);
     RB_REQUIRE(grid.y <= 65535, "refiner_block_small: batch too large");

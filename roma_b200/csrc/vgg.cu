@@ -43,8 +43,15 @@ __global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restr
             for (int t = 0; t < 27; ++t) a = fmaf(in[t], wj[t], a);
             acc[j] = fmaxf(a, 0.f);
         }
+        if constexpr (sizeof(TO) == 2) {      // 8 channels = one 16-byte store
+            TO pk[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[g + j] = from_f<TO>(acc[j]);
+            for (int j = 0; j < 8; ++j) pk[j] = from_f<TO>(acc[j]);
+            *reinterpret_cast<uint4*>(o + g) = *reinterpret_cast<uint4*>(pk);
+        } else {
+            *reinterpret_cast<float4*>(o + g) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(o + g + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
     }
 }
 

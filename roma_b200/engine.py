@@ -134,7 +134,8 @@ class Engine:
         call("romab200_gemm", "rb_gemm_args", **args)
         end.record()
         flops = 2.0 * M * N * K * args["batch0"] * args["batch1"]
-        self.gemm_profile.append(("simt" if args["dtype_ab"] == cabi.RB_F32 else "tcgen05", flops, start, end))
+        self.gemm_profile.append(("simt" if args["dtype_ab"] == cabi.RB_F32 else "tcgen05", flops, start, end,
+                                  (M, N, K, args["batch0"] * args["batch1"])))
 
     def layernorm(self, x, y, gb, rows, cols, eps, dtype_y=None):
         call("romab200_layernorm", "rb_layernorm_args", x=x, y=y, gamma=gb[0], beta=gb[1], rows=rows, cols=cols,
@@ -188,11 +189,12 @@ class Engine:
         es = qkv.element_size()
         q_ptr, k_ptr, v_ptr = qkv.data_ptr(), qkv.data_ptr() + dim * es, qkv.data_ptr() + 2 * dim * es
         # the 1/sqrt(d) scale rides on the QK^T epilogue so that 16-bit scores cannot overflow
-        self.gemm(q_ptr, k_ptr, S, N, N, d, ld, ld, npad, batch0=Bn, batch1=heads, alpha=1.0 / math.sqrt(d),
-                  sa0=N * ld, sa1=d, sb0=N * ld, sb1=d, sc0=heads * N * npad, sc1=N * npad)
-        call("romab200_softmax_rows", "rb_softmax_args", s=S, rows=Bn * heads * N, cols=N, lds=npad, dtype=self.dt, scale=1.0)
-        self.gemm(S, v_ptr, out, N, d, N, npad, ld, dim, trans_b=1, batch0=Bn, batch1=heads,
-                  sa0=heads * N * npad, sa1=N * npad, sb0=N * ld, sb1=d, sc0=N * dim, sc1=d)
+        with self.stage(f"  attn.{tag}"):
+            self.gemm(q_ptr, k_ptr, S, N, N, d, ld, ld, npad, batch0=Bn, batch1=heads, alpha=1.0 / math.sqrt(d),
+                      sa0=N * ld, sa1=d, sb0=N * ld, sb1=d, sc0=heads * N * npad, sc1=N * npad)
+            call("romab200_softmax_rows", "rb_softmax_args", s=S, rows=Bn * heads * N, cols=N, lds=npad, dtype=self.dt, scale=1.0)
+            self.gemm(S, v_ptr, out, N, d, N, npad, ld, dim, trans_b=1, batch0=Bn, batch1=heads,
+                      sa0=heads * N * npad, sa1=N * npad, sb0=N * ld, sb1=d, sc0=N * dim, sc1=d)
 
     def block(self, x, blk, Bn, N, dim, heads, mlp, eps, tag):
         """pre-LN transformer block on the fp32 residual stream x [Bn*N, dim] (block.py:82-107)."""
@@ -259,7 +261,8 @@ class Engine:
         P = self.w.proj[16]
         f32 = cabi.RB_F32
         p16 = self.buf("gp.p16", (E * n, cf), dtype=torch.float32)      # GP runs in fp32 (x.float(), matcher.py:296)
-        self.gemm(feat16, P["w"], p16, E * n, cf, cin, cin, P["w"].shape[1], cf, dtype_c=f32, bias=P["b"])
+        with self.stage("  gp.proj16"):
+            self.gemm(feat16, P["w"], p16, E * n, cf, cin, cin, P["w"].shape[1], cf, dtype_c=f32, bias=P["b"])
         norms = self.buf("gp.norms", (E * n,), dtype=torch.float32)
         call("romab200_row_norms", "rb_rownorm_args", x=p16, out=norms, rows=E * n, cols=cf, ldx=cf, dtype=f32)
         ldw = pad8(n)
@@ -267,12 +270,14 @@ class Engine:
         Wk = self.buf("gp.work", (E, n + nrhs, ldw), dtype=torch.float32)
         stride_w = (n + nrhs) * ldw
         # K_yy + sigma*I for every image (its own features): exp((cos-1)/T)   (matcher.py:191-200, 298, 301)
-        self.gp_kernel_matrix(p16, p16, norms, norms, Wk, n, cf, ldw, batch=E, sa=n * cf, sb=n * cf, sc=stride_w,
-                              sna=n, snb=n, diag=arch.GP_SIGMA_NOISE)
+        with self.stage("  gp.kyy"):
+            self.gp_kernel_matrix(p16, p16, norms, norms, Wk, n, cf, ldw, batch=E, sa=n * cf, sb=n * cf, sc=stride_w,
+                                  sna=n, snb=n, diag=arch.GP_SIGMA_NOISE)
         basis_t = self.gp_basis_t(hp, wp)
         for e in range(E):
             self.copy2d(basis_t, Wk.data_ptr() + (e * stride_w + n * ldw) * 4, nrhs, n, n, ldw, f32, f32)
-        call("romab200_gp_solve", "rb_gp_solve_args", W=Wk, n=n, nrhs=nrhs, batch=E, ldw=ldw, stride=stride_w)
+        with self.stage("  gp.solve"):
+            call("romab200_gp_solve", "rb_gp_solve_args", W=Wk, n=n, nrhs=nrhs, batch=E, ldw=ldw, stride=stride_w)
         # K_xy and mu = K_xy @ alpha for every decoder item: query image i, support image (i + b) % E
         kxy = self.buf("gp.kxy", (D, n, ldw), dtype=torch.float32)
         dim = arch.DEC_DIM
@@ -280,6 +285,7 @@ class Engine:
         es = tokens.element_size()
         halves = [(0, b, b)] if D == b else [(0, b, b), (b, b, 0)]     # (first item, count, first support image)
         for i0, cnt, y0 in halves:
+          with self.stage("  gp.kxy+mu"):
             self.gp_kernel_matrix(p16.data_ptr() + i0 * n * cf * 4, p16.data_ptr() + y0 * n * cf * 4,
                                   norms.data_ptr() + i0 * n * 4, norms.data_ptr() + y0 * n * 4,
                                   kxy.data_ptr() + i0 * n * ldw * 4, n, cf, ldw, batch=cnt, sa=n * cf, sb=n * cf, sc=n * ldw,
@@ -293,15 +299,17 @@ class Engine:
             self.debug["gp.mu"] = tokens.view(D, n, dim)[:, :, :arch.GP_DIM].float().clone()
         x = self.buf("dec.x", (D * n, dim), dtype=torch.float32)
         self.copy2d(tokens, x, D * n, dim, dim, dim, self.dt, f32)
-        for blk in self.w.dec:
-            self.block(x, blk, D, n, dim, arch.DEC_HEADS, arch.DEC_MLP, arch.DEC_LN_EPS, "dec")
+        with self.stage("  dec.blocks"):
+            for blk in self.w.dec:
+                self.block(x, blk, D, n, dim, arch.DEC_HEADS, arch.DEC_MLP, arch.DEC_LN_EPS, "dec")
         xa = self.buf("dec.xa", (D * n, dim))
         self.copy2d(x, xa, D * n, dim, dim, dim, f32, self.dt)
         ldl = pad8(arch.CLS_OUT)
         logits = self.buf("dec.logits", (D * n, ldl), dtype=torch.float32)
-        self.gemm(xa, self.w.to_out_w, logits, D * n, arch.CLS_OUT, dim, dim, dim, ldl, dtype_c=f32, bias=self.w.to_out_b)
-        call("romab200_cls_to_flow_refine", "rb_cls_args", logits=logits, state=state, rows=D * n, ldl=ldl,
-             res=arch.CLS_RES, dtype=f32)
+        with self.stage("  dec.to_out+cls"):
+            self.gemm(xa, self.w.to_out_w, logits, D * n, arch.CLS_OUT, dim, dim, dim, ldl, dtype_c=f32, bias=self.w.to_out_b)
+            call("romab200_cls_to_flow_refine", "rb_cls_args", logits=logits, state=state, rows=D * n, ldl=ldl,
+                 res=arch.CLS_RES, dtype=f32)
         if self.debug is not None:
             self.debug["cls"] = logits.view(D, n, ldl)[:, :, :arch.CLS_OUT].clone()
         # the stride-16 refiner consumes the same projected features (matcher.py:450,484-486)
@@ -322,7 +330,8 @@ class Engine:
         d = self.buf(f"ref.d.{tag}", (D * h * w, cp), zero=True)
         t = self.buf(f"ref.t.{tag}", (D * h * w, cp), zero=True)
         r = spec.radius
-        call("romab200_refiner_prologue", "rb_refiner_prologue_args", feat=feat, ldf=ldf, n_img=E, y_shift=b,
+        with self.stage(f"  prologue{s}.{tag[:2]}"):
+          call("romab200_refiner_prologue", "rb_refiner_prologue_args", feat=feat, ldf=ldf, n_img=E, y_shift=b,
              state=state, d=d, ldd=cp, D=D, h=h, w=w, cf=spec.feat, emb=spec.emb, radius=r, dtype=self.dt,
              emb_weight=R["emb_w"], emb_bias=R["emb_b"],
              disp_scale=float(torch.tensor(40 / 32 * scale_factor, dtype=torch.float32)),

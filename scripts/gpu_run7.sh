@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1_fp16.csv python scripts/profile_one_pass.py fp16 > gpurun_out/prof_pass.log 2>&1; tail -n 2 gpurun_out/prof_pass.log
+python scripts/launch_table.py gpurun_out/launches_r1_fp16.csv | head -50
+timeout 600 python bench.py --precision fp16 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_fp16.json 2> gpurun_out/bench_fp16.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_fp16.json')); print(d['value'], d['ms_per_step']); print(d['stage_ms_per_step'])"
