@@ -94,6 +94,14 @@ int romab200_layernorm(const rb_layernorm_args* args, void* stream);
 typedef struct { void* s; int64_t rows; int32_t cols; int64_t lds; int32_t dtype; float scale; } rb_softmax_args;
 int romab200_softmax_rows(const rb_softmax_args* args, void* stream);
 
+/* Fused attention forward (F.scaled_dot_product_attention, attention.py:50-63), 16-bit tensor-core path:
+ * qkv [batch, n_tokens, ld_qkv] holds q | k | v (each heads*head_dim wide, heads contiguous); out [batch, n_tokens, ld_out].
+ * out[b, i, h*d:(h+1)*d] = softmax_j(q_i . k_j / sqrt(d)) v_j.  head_dim 64 or 128. */
+typedef struct {
+    const void* qkv; void* out; int64_t ld_qkv, ld_out; int32_t batch, n_tokens, heads, head_dim, dtype;
+} rb_flash_attn_args;
+int romab200_flash_attn(const rb_flash_attn_args* args, void* stream);
+
 /* L2 norm of every row: out[r] = ||x[r,:]||  (CosKernel, matcher.py:192-194) */
 typedef struct { const void* x; float* out; int64_t rows; int32_t cols; int64_t ldx; int32_t dtype; } rb_rownorm_args;
 int romab200_row_norms(const rb_rownorm_args* args, void* stream);

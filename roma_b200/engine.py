@@ -50,6 +50,7 @@ class Engine:
         self._buf: Dict[tuple, torch.Tensor] = {}
         self._const: Dict[tuple, torch.Tensor] = {}
         self.debug: Optional[dict] = None        # set to {} to keep stage tensors (tests)
+        self.use_flash_attn = True               # fused tcgen05 attention in the 16-bit modes (else QK^T / softmax / PV GEMMs)
         self.profile: Optional[dict] = None      # set to {} to collect CUDA-event timings per stage (bench.py)
         self.gemm_profile: Optional[list] = None  # set to [] to time every GEMM launch: (backend, flops, start, end)
 
@@ -182,6 +183,11 @@ class Engine:
         """softmax(q k^T / sqrt(d)) v per head (F.scaled_dot_product_attention, attention.py:50-63).
         qkv [Bn, N, 3*dim] (q|k|v, heads contiguous inside each) -> out [Bn, N, dim]."""
         d = dim // heads
+        if self.dtype != torch.float32 and self.use_flash_attn:
+            with self.stage(f"  attn.{tag}"):
+                call("romab200_flash_attn", "rb_flash_attn_args", qkv=qkv, out=out, ld_qkv=3 * dim, ld_out=dim, batch=Bn, n_tokens=N,
+                     heads=heads, head_dim=d, dtype=self.dt)
+            return
         npad = pad8(N)
         sdt = self.dtype
         S = self.buf(f"attn.scores.{tag}", (Bn, heads, N, npad), dtype=sdt)

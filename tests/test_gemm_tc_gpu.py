@@ -147,3 +147,17 @@ def test_refiner_block_small_fused_vs_unfused(dt):
     call("romab200_refiner_block_small", "rb_refiner_block_small_args", **{"in": xi}, out=out, ld=C, dw_weight=dwt, ldw=C, dw_bias=db,
          pw_weight=pw.float().contiguous(), pw_bias=pb, batch=B, h=H, w=W, c=C, dtype=CODE[dt])
     close(out, ref, 6e-2 if dt == torch.bfloat16 else 8e-3)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("H,d,N,Bn", [(16, 64, 1601, 2), (8, 128, 1600, 2), (3, 64, 77, 1), (2, 128, 300, 3), (2, 64, 128, 1)])
+def test_flash_attn(dt, H, d, N, Bn):
+    dim = H * d
+    qkv = rnd(Bn, N, 3 * dim, seed=1, dtype=dt, scale=1.0)
+    out = torch.full((Bn, N, dim), 9.0, dtype=dt, device=DEV)
+    call("romab200_flash_attn", "rb_flash_attn_args", qkv=qkv, out=out, ld_qkv=3 * dim, ld_out=dim, batch=Bn, n_tokens=N, heads=H,
+         head_dim=d, dtype=CODE[dt])
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().reshape(Bn, N, 3, H, d).unbind(2)
+    ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2).reshape(Bn, N, dim)
+    close(out, ref, 2.5e-2 if dt == torch.bfloat16 else 4e-3)
