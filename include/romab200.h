@@ -146,7 +146,10 @@ int romab200_assemble_tokens(const rb_tokens_args* args, void* stream);
  * K_yy + sigma*I (lower triangle is read), rows n.. hold F^T ([nrhs, n]).  On return rows n.. hold
  * X^T where (K_yy + sigma I) X = F, i.e. alpha^T, ready to be the [N,K] operand of mu = K_xy @ alpha.
  * Replaces torch.linalg.cholesky + torch.cholesky_solve (matcher.py:307-308). */
-typedef struct { float* W; int32_t n, nrhs, batch; int64_t ldw, stride; } rb_gp_solve_args;
+typedef struct {
+    float* W; int32_t n, nrhs, batch; int64_t ldw, stride;
+    void* workspace; int64_t workspace_bytes;   /* optional: >= (batch*ceil(n/32)*1024 + 1)*4 bytes -> single persistent cooperative launch */
+} rb_gp_solve_args;
 int romab200_gp_solve(const rb_gp_solve_args* args, void* stream);
 /* ---- classifier head -> coarse flow (utils.py:300-322) ------------------------------------------
  * logits [rows, ldl] fp32/16 with 4096 anchor logits followed by the certainty logit; writes

@@ -123,11 +123,16 @@ struct TcParams {
 constexpr int TC_BM = 128, TC_BK = 64;
 
 template <int BN> struct TcCfg {
-    static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);   // BN<=128: ~96 KB -> 2 CTAs / SM
+    // BN = 256: one CTA per SM with 8 epilogue warps; narrower tiles: two CTAs per SM (two MMA-issuing threads keep the
+    // tensor pipe fed when a k-block is only 128-256 MMA cycles) with 4 epilogue warps each
+    static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);
     static constexpr int CTAS_PER_SM = BN >= 256 ? 1 : 2;
+    static constexpr int EPI_WARPS = BN >= 256 ? 8 : 4;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;
     static constexpr int B_BYTES = BN * TC_BK * 2;
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int EPI_BYTES = 2 * 256 * 4;                        // staged bias / column-scale (or norm_b) of the tile
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // two accumulator stages
 };
 
@@ -139,7 +144,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // together share the same weight tile in L2).  The accumulator is double-buffered in TMEM: the MMA warp starts the
 // next tile while the epilogue warps drain the previous one.
 template <int BN>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+__global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                          const TcParams p) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -152,6 +157,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     uint64_t* tmem_full_bar = empty_bar + STAGES;       // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    float* s_vec0 = reinterpret_cast<float*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES) + 256);   // bias      | norm_b
+    float* s_vec1 = s_vec0 + 256;                                                                     // col_scale
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = (p.K + TC_BK - 1) / TC_BK;
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], Cfg::EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -234,26 +241,37 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             }
         }
     } else {
-        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+        // ===== epilogue (warps 2..9): TMEM lane quarter = warp % 4; the two warps of a quarter split the column chunks =====
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;                      // 0..255 among the epilogue threads
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
             const int z = tile / tiles_per_z, r = tile - z * tiles_per_z;
             const int nt = r / p.tiles_m, mt = r - nt * p.tiles_m;
             const int m0 = mt * TC_BM, n0 = nt * BN, z0 = z / p.batch1, z1 = z - z0 * p.batch1;
             const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
-            mbar_wait(&tmem_full_bar[acc], acc_ph);
-            tc_fence_after();
             Epilogue e = p.epi;
             e.C = (char*)e.C + (z0 * p.sc0 + z1 * p.sc1) * dtype_size(e.dtype_c);
             if (e.R) e.R = (const char*)e.R + (z0 * p.sr0 + z1 * p.sr1) * dtype_size(e.dtype_r);
             if (e.norm_a) e.norm_a += z0 * p.sna0;
             if (e.norm_b) e.norm_b += z0 * p.snb0;
+            // stage the per-column epilogue vectors of this tile in shared memory (read back as broadcast float4s)
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");   // everyone is done with the previous tile's vectors
+            for (int t = et; t < BN; t += 32 * Cfg::EPI_WARPS) {
+                const int n = n0 + t;
+                const float* v0 = e.epi == RB_EPI_COSKERNEL ? e.norm_b : e.bias;
+                s_vec0[t] = (v0 && n < p.N) ? v0[n] : (e.epi == RB_EPI_COSKERNEL ? 1.f : 0.f);
+                s_vec1[t] = (e.col_scale && n < p.N) ? e.col_scale[n] : 1.f;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");
+            mbar_wait(&tmem_full_bar[acc], acc_ph);
+            tc_fence_after();
             const int m = m0 + q * 32 + lane;
             const int64_t orow = m < p.M ? e.map_row(m) : -1;
             const bool vec_ok = (e.ldc * dtype_size(e.dtype_c)) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.C) % 16 == 0);
 #pragma unroll 1
-            for (int cb = 0; cb < BN; cb += 32) {
+            for (int cb = half * 32; cb < BN; cb += 8 * Cfg::EPI_WARPS) {
                 if (n0 + cb >= p.N) break;                     // warp-uniform
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cb, v);
@@ -266,7 +284,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int n = nb + j;
-                        const float pn = na * (n < p.N ? e.norm_b[n] : 1.f);
+                        const float pn = na * s_vec0[cb + j];
                         const float sc = e.cos_normalized ? pn / (pn + e.eps) : 1.0f / (pn + e.eps);
                         float r = expf((v[j] * sc - 1.0f) * e.inv_t);
                         if (m == n) r += e.diag_add;
@@ -278,10 +296,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                         for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
                     }
                     if (e.bias) {
-                        float bv[32];
-                        load_row32(e.bias + nb, bv, full, p.N - nb);
     #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += bv[j];
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(&s_vec0[cb + 4 * j]);
+                            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                        }
                     }
                     if (e.act == RB_ACT_RELU) {
     #pragma unroll
@@ -291,10 +310,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
                     if (e.col_scale) {
-                        float sv[32];
-                        load_row32(e.col_scale + nb, sv, full, p.N - nb);
     #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= sv[j];
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(&s_vec1[cb + 4 * j]);
+                            v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
+                        }
                     }
                     if (e.R) {
                         if (e.dtype_r == RB_F32) {
@@ -309,13 +329,19 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                         }
                     }
                 }
-                if (vec_ok && nb + 32 <= p.N) {
+                if (vec_ok) {
                     if (e.dtype_c == RB_F32) {
-                        float4* dst = reinterpret_cast<float4*>((float*)e.C + orow * e.ldc + nb);
+                        float* dst = (float*)e.C + orow * e.ldc + nb;
     #pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int j = 0; j < 8; ++j) {
+                            if (nb + 4 * j + 4 <= p.N) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            else {
+    #pragma unroll
+                                for (int t = 0; t < 4; ++t) if (nb + 4 * j + t < p.N) dst[4 * j + t] = v[4 * j + t];
+                            }
+                        }
                     } else {
-                        uint4* dst = reinterpret_cast<uint4*>((uint16_t*)e.C + orow * e.ldc + nb);
+                        uint16_t* dst = (uint16_t*)e.C + orow * e.ldc + nb;
     #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint32_t w[4];
@@ -325,7 +351,12 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                                 if (e.dtype_c == RB_F16) { __half2 h = __floats2half2_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
                                 else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
                             }
-                            dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                            if (nb + 8 * j + 8 <= p.N) *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+                            else {
+    #pragma unroll
+                                for (int t = 0; t < 8; ++t)
+                                    if (nb + 8 * j + t < p.N) dst[8 * j + t] = (uint16_t)(w[t >> 1] >> (16 * (t & 1)));
+                            }
                         }
                     }
                 } else {
@@ -407,7 +438,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, 
     p.total_tiles = (int)total;
     const int resident = sm_count() * Cfg::CTAS_PER_SM;
     const int grid = p.total_tiles < resident ? p.total_tiles : resident;
-    gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM, st>>>(ma, mb, p);
+    gemm_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(ma, mb, p);
     return check_launch("gemm_tc");
 }
 

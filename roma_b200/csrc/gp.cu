@@ -23,7 +23,7 @@ __device__ void factor_diag_block(const float* __restrict__ Wd, int64_t ldw, int
 #pragma unroll
     for (int c = 0; c < NB; ++c) {
         float v = 0.f;
-        if (lane < bs && c < bs && c <= lane) v = Wd[(int64_t)lane * ldw + c];
+        if (lane < bs && c < bs && c <= lane) v = __ldcg(Wd + (int64_t)lane * ldw + c);
         if (c == lane && lane >= bs) v = 1.f;      // identity padding
         r[c] = v;
     }
@@ -113,6 +113,231 @@ __global__ void __launch_bounds__(128) trsm_back_kernel(float* __restrict__ W, i
         if (c < bs) yr[c] = y[c];
 }
 
+// --------------------------------------------------------------------------------------------------
+// Persistent single-launch variant: the whole factorisation + both substitutions in ONE cooperative kernel.
+// The multi-kernel version above spends its time in ~250 dependent launches of a few microseconds each; here all
+// CTAs stay resident and step through the same phases separated by a device-wide barrier (one atomic counter,
+// release/acquire fences).  Per 32-wide panel: phase A = every CTA that owns panel rows re-factors the 32x32
+// diagonal block in shared memory (one warp, shuffles) and solves its 64 rows; phase B = 64x64 tiles of the
+// rank-32 trailing update spread over all CTAs.  Diagonal factors go to a side buffer (`diag`) so that nobody
+// overwrites a block other CTAs are still reading.
+// --------------------------------------------------------------------------------------------------
+struct GpPersistParams {
+    float* W; float* diag; unsigned int* counter;
+    int n, nrhs, batch;
+    int64_t ldw, stride;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();                              // release: this CTA's writes are visible device-wide
+        atomicAdd(counter, 1u);
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+        __threadfence();                              // acquire + L1 invalidate for the loads that follow
+    }
+    __syncthreads();
+}
+
+constexpr int GP_THREADS = 128;     // lean CTAs: the kernel is latency-bound and should leave the SMs to concurrent GEMM CTAs
+
+__global__ void __launch_bounds__(GP_THREADS) gp_solve_persistent_kernel(const GpPersistParams p) {
+    __shared__ float L[NB][NB + 1];
+    __shared__ float Pi[64][NB + 1];
+    __shared__ float Pj[64][NB + 1];
+    const int tid = threadIdx.x;
+    const int n = p.n, total = p.n + p.nrhs;
+    const int nblk = (n + NB - 1) / NB;
+    unsigned int target = 0;
+
+    // ================= factorisation + forward substitution =================
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k = kb * NB, bs = min(NB, n - k);
+        const int below = total - (k + bs);
+        const int nchunks = (below + 63) / 64;
+        // ---- phase A
+        int loaded_e = -1;
+        for (int item = blockIdx.x; item < p.batch * nchunks; item += gridDim.x) {
+            const int e = item / nchunks, c = item - e * nchunks;
+            float* Wb = p.W + (int64_t)e * p.stride;
+            if (e != loaded_e) {
+                __syncthreads();
+                if (tid < 32) factor_diag_block(Wb + (int64_t)k * p.ldw + k, p.ldw, bs, L, nullptr);
+                __syncthreads();
+                loaded_e = e;
+            }
+            if (c == 0) {                                   // publish L_kk for the backward pass
+                float* dst = p.diag + ((int64_t)e * nblk + kb) * NB * NB;
+                for (int i = tid; i < NB * NB; i += GP_THREADS) dst[i] = L[i / NB][i % NB];
+            }
+            const int row = k + bs + c * 64 + tid;
+            if (tid < 64 && row < total) {
+                float* ar = Wb + (int64_t)row * p.ldw + k;
+                float a[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) a[q] = q < bs ? __ldcg(ar + q) : 0.f;
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    float x = a[j] / L[j][j];
+                    a[j] = x;
+#pragma unroll
+                    for (int q = j + 1; q < NB; ++q) a[q] = fmaf(-x, L[q][j], a[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+                    if (q < bs) ar[q] = a[q];
+            }
+        }
+        grid_barrier(p.counter, target);
+        // ---- phase B: C[i, j] -= sum_p P[i, p] P[j, p] on rows/cols beyond the panel
+        const int r0 = k + bs;
+        const int nt = n - r0;                              // trailing columns
+        if (nt > 0) {
+            const int tiles_i = (total - r0 + 63) / 64, tiles_j = (nt + 63) / 64;
+            for (int item = blockIdx.x; item < p.batch * tiles_i * tiles_j; item += gridDim.x) {
+                const int e = item / (tiles_i * tiles_j), t = item - e * (tiles_i * tiles_j);
+                const int ti = t / tiles_j, tj = t - ti * tiles_j;
+                const int i0 = r0 + ti * 64, j0 = r0 + tj * 64;
+                if (i0 + 63 < n && j0 > i0 + 63) continue;  // whole tile strictly above the diagonal of the SPD part: never read
+                float* Wb = p.W + (int64_t)e * p.stride;
+                __syncthreads();
+                for (int idx = tid; idx < 64 * NB; idx += GP_THREADS) {
+                    const int r = idx / NB, q = idx - r * NB;
+                    Pi[r][q] = (i0 + r < total && q < bs) ? __ldcg(Wb + (int64_t)(i0 + r) * p.ldw + k + q) : 0.f;
+                    Pj[r][q] = (j0 + r < n && q < bs) ? __ldcg(Wb + (int64_t)(j0 + r) * p.ldw + k + q) : 0.f;
+                }
+                __syncthreads();
+                const int tr = (tid / 16) * 8, tc = (tid % 16) * 4;
+                float acc[8][4];
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    float av[8], bv[4];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) av[a] = Pi[tr + a][q];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) bv[a] = Pj[tc + a][q];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+                }
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const int r = i0 + tr + a;
+                    if (r >= total) continue;
+                    float* cp = Wb + (int64_t)r * p.ldw + j0 + tc;
+                    if (j0 + tc + 3 < n) {
+                        float4 v = __ldcg(reinterpret_cast<const float4*>(cp));
+                        v.x -= acc[a][0]; v.y -= acc[a][1]; v.z -= acc[a][2]; v.w -= acc[a][3];
+                        *reinterpret_cast<float4*>(cp) = v;
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if (j0 + tc + b < n) cp[b] = __ldcg(cp + b) - acc[a][b];
+                    }
+                }
+            }
+            grid_barrier(p.counter, target);
+        }
+    }
+    // ================= backward substitution on the RHS rows: X^T L = Y^T =================
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int k = kb * NB, bs = min(NB, n - k);
+        const int nchunks = (p.nrhs + 63) / 64;
+        int loaded_e = -1;
+        for (int item = blockIdx.x; item < p.batch * nchunks; item += gridDim.x) {
+            const int e = item / nchunks, c = item - e * nchunks;
+            float* Wb = p.W + (int64_t)e * p.stride;
+            if (e != loaded_e) {
+                __syncthreads();
+                const float* src = p.diag + ((int64_t)e * nblk + kb) * NB * NB;
+                for (int i = tid; i < NB * NB; i += GP_THREADS) L[i / NB][i % NB] = __ldcg(src + i);
+                __syncthreads();
+                loaded_e = e;
+            }
+            const int r = c * 64 + tid;
+            if (tid < 64 && r < p.nrhs) {
+                float* yr = Wb + (int64_t)(n + r) * p.ldw + k;
+                float y[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) y[q] = q < bs ? __ldcg(yr + q) : 0.f;
+#pragma unroll
+                for (int j = NB - 1; j >= 0; --j) {
+                    float x = y[j] / L[j][j];
+                    y[j] = x;
+#pragma unroll
+                    for (int q = 0; q < j; ++q) y[q] = fmaf(-x, L[j][q], y[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+                    if (q < bs) yr[q] = y[q];
+            }
+        }
+        if (k == 0) break;
+        grid_barrier(p.counter, target);
+        // Y[:, 0:k] -= X[:, k:k+bs] . L[k:k+bs, 0:k]
+        const int tiles_i = (p.nrhs + 63) / 64, tiles_j = (k + 63) / 64;
+        for (int item = blockIdx.x; item < p.batch * tiles_i * tiles_j; item += gridDim.x) {
+            const int e = item / (tiles_i * tiles_j), t = item - e * (tiles_i * tiles_j);
+            const int ti = t / tiles_j, tj = t - ti * tiles_j;
+            const int i0 = ti * 64, j0 = tj * 64;
+            float* Wb = p.W + (int64_t)e * p.stride;
+            __syncthreads();
+            for (int idx = tid; idx < 64 * NB; idx += GP_THREADS) {
+                const int r = idx / NB, q = idx - r * NB;
+                Pi[r][q] = (i0 + r < p.nrhs && q < bs) ? __ldcg(Wb + (int64_t)(n + i0 + r) * p.ldw + k + q) : 0.f;
+            }
+            for (int idx = tid; idx < NB * 64; idx += GP_THREADS) {           // L rows k..k+bs, columns j0..j0+63 -> Pj[col][p]
+                const int q = idx / 64, cidx = idx - q * 64;
+                Pj[cidx][q] = (q < bs && j0 + cidx < k) ? __ldcg(Wb + (int64_t)(k + q) * p.ldw + j0 + cidx) : 0.f;
+            }
+            __syncthreads();
+            const int tr = (tid / 16) * 8, tc = (tid % 16) * 4;
+            float acc[8][4];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                float av[8], bv[4];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) av[a] = Pi[tr + a][q];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) bv[a] = Pj[tc + a][q];
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int r = i0 + tr + a;
+                if (r >= p.nrhs) continue;
+                float* cp = Wb + (int64_t)(n + r) * p.ldw + j0 + tc;
+                if (j0 + tc + 3 < k) {
+                    float4 v = __ldcg(reinterpret_cast<const float4*>(cp));
+                    v.x -= acc[a][0]; v.y -= acc[a][1]; v.z -= acc[a][2]; v.w -= acc[a][3];
+                    *reinterpret_cast<float4*>(cp) = v;
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (j0 + tc + b < k) cp[b] = __ldcg(cp + b) - acc[a][b];
+                }
+            }
+        }
+        grid_barrier(p.counter, target);
+    }
+}
+
 static int sub_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int trans_b, float* C, int64_t ldc, int M, int N, int K,
                     int batch, int64_t stride, cudaStream_t st) {
     rb_gemm_args g = {};
@@ -131,6 +356,27 @@ extern "C" int romab200_gp_solve(const rb_gp_solve_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->n > 0 && a->nrhs > 0 && a->batch > 0 && a->ldw >= a->n, "gp_solve: bad shape n=%d nrhs=%d batch=%d", a->n, a->nrhs, a->batch);
     RB_REQUIRE(a->batch <= 65535, "gp_solve: batch too large");
+    if (a->workspace) {
+        // single cooperative launch; workspace = [batch * ceil(n/32) * 1024 floats of diagonal factors | 1 counter word]
+        RB_REQUIRE(a->ldw % 4 == 0 && ((uintptr_t)a->W) % 16 == 0, "gp_solve: W must be 16-byte aligned with ldw %% 4 == 0");
+        const int64_t nblk = (a->n + NB - 1) / NB;
+        const int64_t diag_floats = (int64_t)a->batch * nblk * NB * NB;
+        RB_REQUIRE(a->workspace_bytes >= (diag_floats + 1) * 4, "gp_solve: workspace too small (%lld < %lld bytes)",
+                   (long long)a->workspace_bytes, (long long)(diag_floats + 1) * 4);
+        GpPersistParams p;
+        p.W = a->W; p.diag = (float*)a->workspace; p.counter = (unsigned int*)((float*)a->workspace + diag_floats);
+        p.n = a->n; p.nrhs = a->nrhs; p.batch = a->batch; p.ldw = a->ldw; p.stride = a->stride;
+        RB_REQUIRE(cudaMemsetAsync(p.counter, 0, 4, st) == cudaSuccess, "gp_solve: memset failed");
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gp_solve_persistent_kernel, GP_THREADS, 0);
+        RB_REQUIRE(sms > 0 && per_sm > 0, "gp_solve: cannot size the cooperative grid");
+        void* kargs[] = {(void*)&p};
+        cudaError_t err = cudaLaunchCooperativeKernel((void*)gp_solve_persistent_kernel, dim3(sms), dim3(GP_THREADS), kargs, 0, st);
+        RB_REQUIRE(err == cudaSuccess, "gp_solve: cooperative launch failed: %s", cudaGetErrorString(err));
+        return check_launch("gp_solve_persistent");
+    }
     const int n = a->n, total = a->n + a->nrhs;
     float* W = a->W;
     // factorisation + forward substitution on the augmented rows

@@ -51,6 +51,11 @@ class Engine:
         self._const: Dict[tuple, torch.Tensor] = {}
         self.debug: Optional[dict] = None        # set to {} to keep stage tensors (tests)
         self.use_flash_attn = True               # fused tcgen05 attention in the 16-bit modes (else QK^T / softmax / PV GEMMs)
+        self.gp_persistent = False               # True: GP Cholesky + solves as one cooperative persistent kernel (measured: no
+                                                 # faster than the launch chain, and cooperative launches do not overlap the CNN branch)
+        self.overlap_cnn = True                  # VGG/proj branch on a side stream, overlapping ViT / GP / decoder
+        self.gp_tensor_core = True               # all-pairs CosKernel on tcgen05 (split-fp16 operands) in the 16-bit modes
+        self._side = None
         self.profile: Optional[dict] = None      # set to {} to collect CUDA-event timings per stage (bench.py)
         self.gemm_profile: Optional[list] = None  # set to [] to time every GEMM launch: (backend, flops, start, end)
 
@@ -276,14 +281,30 @@ class Engine:
         Wk = self.buf("gp.work", (E, n + nrhs, ldw), dtype=torch.float32)
         stride_w = (n + nrhs) * ldw
         # K_yy + sigma*I for every image (its own features): exp((cos-1)/T)   (matcher.py:191-200, 298, 301)
+        tc_kernel = self.dtype != torch.float32 and self.gp_tensor_core
+        if tc_kernel:
+            # all-pairs CosKernel on the f16 tensor pipe with fp32-class accuracy: L2-normalised rows split into fp16
+            # hi/lo parts, A' = [hi|lo|hi], B' = [hi|hi|lo]  ->  A'.B'^T = hi.hi + lo.hi + hi.lo  (K' = 3*512)
+            xa = self.buf("gp.split_a", (E * n, 3 * cf), dtype=torch.float16)
+            xb = self.buf("gp.split_b", (E * n, 3 * cf), dtype=torch.float16)
+            with self.stage("  gp.split"):
+                call("romab200_split_f16x3", "rb_split_args", x=p16, dst=xa, rows=E * n, cols=cf, ldx=cf, ldd=3 * cf, row_norm=norms, layout_b=0)
+                call("romab200_split_f16x3", "rb_split_args", x=p16, dst=xb, rows=E * n, cols=cf, ldx=cf, ldd=3 * cf, row_norm=norms, layout_b=1)
         with self.stage("  gp.kyy"):
-            self.gp_kernel_matrix(p16, p16, norms, norms, Wk, n, cf, ldw, batch=E, sa=n * cf, sb=n * cf, sc=stride_w,
-                                  sna=n, snb=n, diag=arch.GP_SIGMA_NOISE)
+            if tc_kernel:
+                self.gp_kernel_matrix_tc(xa, xb, norms, norms, Wk, n, cf, ldw, batch=E, sa=n * 3 * cf, sb=n * 3 * cf, sc=stride_w,
+                                         sna=n, snb=n, diag=arch.GP_SIGMA_NOISE)
+            else:
+                self.gp_kernel_matrix(p16, p16, norms, norms, Wk, n, cf, ldw, batch=E, sa=n * cf, sb=n * cf, sc=stride_w,
+                                      sna=n, snb=n, diag=arch.GP_SIGMA_NOISE)
         basis_t = self.gp_basis_t(hp, wp)
         for e in range(E):
             self.copy2d(basis_t, Wk.data_ptr() + (e * stride_w + n * ldw) * 4, nrhs, n, n, ldw, f32, f32)
         with self.stage("  gp.solve"):
-            call("romab200_gp_solve", "rb_gp_solve_args", W=Wk, n=n, nrhs=nrhs, batch=E, ldw=ldw, stride=stride_w)
+            ws_bytes = (E * ((n + 31) // 32) * 1024 + 1) * 4
+            ws = self.buf("gp.solve_ws", (ws_bytes // 4,), dtype=torch.float32)
+            call("romab200_gp_solve", "rb_gp_solve_args", W=Wk, n=n, nrhs=nrhs, batch=E, ldw=ldw, stride=stride_w,
+                 workspace=ws if self.gp_persistent else None, workspace_bytes=ws_bytes if self.gp_persistent else 0)
         # K_xy and mu = K_xy @ alpha for every decoder item: query image i, support image (i + b) % E
         kxy = self.buf("gp.kxy", (D, n, ldw), dtype=torch.float32)
         dim = arch.DEC_DIM
@@ -292,10 +313,16 @@ class Engine:
         halves = [(0, b, b)] if D == b else [(0, b, b), (b, b, 0)]     # (first item, count, first support image)
         for i0, cnt, y0 in halves:
           with self.stage("  gp.kxy+mu"):
-            self.gp_kernel_matrix(p16.data_ptr() + i0 * n * cf * 4, p16.data_ptr() + y0 * n * cf * 4,
-                                  norms.data_ptr() + i0 * n * 4, norms.data_ptr() + y0 * n * 4,
-                                  kxy.data_ptr() + i0 * n * ldw * 4, n, cf, ldw, batch=cnt, sa=n * cf, sb=n * cf, sc=n * ldw,
-                                  sna=n, snb=n, diag=0.0)
+            if tc_kernel:
+                self.gp_kernel_matrix_tc(xa.data_ptr() + i0 * n * 3 * cf * 2, xb.data_ptr() + y0 * n * 3 * cf * 2,
+                                         norms.data_ptr() + i0 * n * 4, norms.data_ptr() + y0 * n * 4,
+                                         kxy.data_ptr() + i0 * n * ldw * 4, n, cf, ldw, batch=cnt, sa=n * 3 * cf, sb=n * 3 * cf,
+                                         sc=n * ldw, sna=n, snb=n, diag=0.0)
+            else:
+                self.gp_kernel_matrix(p16.data_ptr() + i0 * n * cf * 4, p16.data_ptr() + y0 * n * cf * 4,
+                                      norms.data_ptr() + i0 * n * 4, norms.data_ptr() + y0 * n * 4,
+                                      kxy.data_ptr() + i0 * n * ldw * 4, n, cf, ldw, batch=cnt, sa=n * cf, sb=n * cf, sc=n * ldw,
+                                      sna=n, snb=n, diag=0.0)
             self.gemm(kxy.data_ptr() + i0 * n * ldw * 4, Wk.data_ptr() + (y0 * stride_w + n * ldw) * 4,
                       tokens.data_ptr() + i0 * n * dim * es, n, nrhs, n, ldw, ldw, dim, dtype_ab=f32,
                       batch0=cnt, sa0=n * ldw, sb0=stride_w, sc0=n * dim)
@@ -328,6 +355,12 @@ class Engine:
         self.gemm(A, B, C, n, n, cf, cf, cf, ldc, dtype_ab=cabi.RB_F32, dtype_c=cabi.RB_F32, batch0=batch,
                   sa0=sa, sb0=sb, sc0=sc, epi=cabi.EPI_COSKERNEL, norm_a=na, norm_b=nb, sna0=sna, snb0=snb,
                   eps=arch.GP_COS_EPS, inv_t=1.0 / arch.GP_TEMPERATURE, diag_add=diag, cos_normalized=0)
+
+    def gp_kernel_matrix_tc(self, A, B, na, nb, C, n, cf, ldc, batch, sa, sb, sc, sna, snb, diag):
+        """Same contraction on tcgen05 from the split fp16 operands (pre-normalised rows: cos_normalized=1)."""
+        self.gemm(A, B, C, n, n, 3 * cf, 3 * cf, 3 * cf, ldc, dtype_ab=cabi.RB_F16, dtype_c=cabi.RB_F32, batch0=batch,
+                  sa0=sa, sb0=sb, sc0=sc, epi=cabi.EPI_COSKERNEL, norm_a=na, norm_b=nb, sna0=sna, snb0=snb,
+                  eps=arch.GP_COS_EPS, inv_t=1.0 / arch.GP_TEMPERATURE, diag_add=diag, cos_normalized=1)
 
     # ------------------------------------------------------------------ ConvRefiner (matcher.py:124-179)
     def refine(self, s, feat, ldf, E, D, b, h, w, state, scale_factor, h1, w1, tag):
@@ -370,20 +403,39 @@ class Engine:
         return dst
 
     # ------------------------------------------------------------------ one pass of the matcher
+    def encode_cnn(self, images: torch.Tensor, tag: str):
+        """VGG19 pyramid + proj[s] of one pass: {s: (projected channels-last features, pitch)}, {s: (h, w)}."""
+        E = images.shape[0]
+        with self.stage(f"vgg.{tag}"):
+            taps = self.vgg(images, tag)
+        sizes = {s: (taps[s][1], taps[s][2]) for s in (1, 2, 4, 8)}
+        feats = {}
+        for s in (8, 4, 2, 1):
+            h, w = sizes[s]
+            with self.stage(f"proj{s}.{tag}"):
+                feats[s] = (self.proj_from_padded(s, taps[s][0], E, h, w, tag), pad8(arch.PROJ[s][1]))
+        return feats, sizes
+
     def run_pass(self, images: torch.Tensor, b: int, symmetric: bool, upsample: bool, scale_factor: float,
-                 state_in: Optional[Tuple[torch.Tensor, int, int]] = None, keep_states=False):
-        """images [2b,3,H,W] fp32 (A batch then B batch).  Returns (state [D,H,W,3], states per scale)."""
+                 state_in: Optional[Tuple[torch.Tensor, int, int]] = None, keep_states=False, cnn=None, cnn_ready=None, vit=None):
+        """images [2b,3,H,W] fp32 (A batch then B batch).  Returns (state [D,H,W,3], states per scale, sizes).
+        `cnn` = result of `encode_cnn` computed elsewhere (side stream); `cnn_ready` = event to wait for before use."""
         tag = "up" if upsample else "lo"
         E = 2 * b
         D = E if symmetric else b
         _, _, H, W = images.shape
-        with self.stage(f"vgg.{tag}"):
-            taps = self.vgg(images, tag)
-        sizes = {s: (taps[s][1], taps[s][2]) for s in (1, 2, 4, 8)}
+        if cnn is None and (upsample or vit is None):
+            cnn = self.encode_cnn(images, tag)
+        if not upsample and vit is None:
+            with self.stage("dinov2"):
+                vit = self.dinov2(images)
+        if cnn is None:
+            cnn = self.encode_cnn(images, tag)
+        feats, sizes = cnn
+        sizes = dict(sizes)
         states = {}
         if not upsample:
-            with self.stage("dinov2"):
-                feat16_raw, hp, wp = self.dinov2(images)
+            feat16_raw, hp, wp = vit
             sizes[16] = (hp, wp)
             state = self.buf("state.lo.16", (D, hp, wp, 3), dtype=torch.float32)
             with self.stage("gp+decoder"):
@@ -400,9 +452,10 @@ class Engine:
             if s == 16:
                 feat, ldf = feat16, arch.PROJ[16][1]
             else:
-                with self.stage(f"proj{s}.{tag}"):
-                    feat = self.proj_from_padded(s, taps[s][0], E, h, w, tag)
-                ldf = pad8(arch.PROJ[s][1])
+                if cnn_ready is not None:
+                    torch.cuda.current_stream().wait_event(cnn_ready)
+                    cnn_ready = None
+                feat, ldf = feats[s]
             if self.debug is not None:
                 self.debug[f"{tag}.proj{s}"] = feat.view(E, h, w, -1)[..., :arch.PROJ[s][1]].float().clone()
             with self.stage(f"refine{s}.{tag}"):
@@ -413,6 +466,40 @@ class Engine:
                 ho, wo = sizes[s // 2]
                 state = self.resize_state(state, D, h, w, ho, wo, name=f"state.{tag}.{s // 2}")
         return state, states, sizes
+
+    def run_match(self, images, images_hi, b, symmetric, scale_lo, scale_hi, attenuate, warp, cert):
+        """Device side of match(): coarse pass, optional upsample pass, epilogue — no allocation, no host sync.
+        The CNN branch (VGG19 + proj of both passes) has no dependency on the ViT / GP / decoder chain, so it runs on a
+        side stream and overlaps the latency-bound GP solve and decoder; under CUDA-graph capture this becomes a fork."""
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        side = self._side
+        overlap = self.overlap_cnn and self.debug is None
+        cnn_lo = cnn_hi = ev_lo = ev_hi = vit = None
+        if overlap:
+            # the ViT saturates the tensor pipe by itself; the CNN branch is released when it finishes, so that it
+            # fills the SMs left idle by the latency-bound GP solve and the small decoder GEMMs that follow
+            with self.stage("dinov2"):
+                vit = self.dinov2(images)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                cnn_lo = self.encode_cnn(images, "lo")
+                ev_lo = torch.cuda.Event()
+                ev_lo.record(side)
+                if images_hi is not None:
+                    cnn_hi = self.encode_cnn(images_hi, "up")
+                    ev_hi = torch.cuda.Event()
+                    ev_hi.record(side)
+        hs, ws = images.shape[-2:]
+        state, states, sizes = self.run_pass(images, b, symmetric, False, scale_lo, cnn=cnn_lo, cnn_ready=ev_lo, vit=vit)
+        coarse = states[16] if attenuate else None
+        hc, wc = sizes[16]
+        if images_hi is not None:
+            hh, wh = images_hi.shape[-2:]
+            state, _, _ = self.run_pass(images_hi, b, symmetric, True, scale_hi, (state, hs, ws), cnn=cnn_hi, cnn_ready=ev_hi)
+            hs, ws = hh, wh
+        self.epilogue(state, coarse, hc, wc, b, hs, ws, symmetric, out=(warp, cert))
 
     def epilogue(self, state, coarse_state, hc, wc, b, H, W, symmetric, out=None):
         Wout = 2 * W if symmetric else W

@@ -141,17 +141,8 @@ class RegressionMatcher:
 
     def _run_device(self, images, images_hi, b, symmetric, scale_factor, attenuate, warp, cert):
         """Both passes + epilogue on the current stream; no allocation, no host sync (CUDA-graph capturable)."""
-        eng = self.engine
-        hs, ws = images.shape[-2:]
-        state, states, sizes = eng.run_pass(images, b, symmetric, False, scale_factor)
-        coarse = states[16] if attenuate else None
-        hc, wc = sizes[16]
-        if images_hi is not None:
-            hh, wh = images_hi.shape[-2:]
-            sf = math.sqrt(self.upsample_res[0] * self.upsample_res[1] / (560 ** 2))
-            state, _, _ = eng.run_pass(images_hi, b, symmetric, True, sf, (state, hs, ws))
-            hs, ws = hh, wh
-        eng.epilogue(state, coarse, hc, wc, b, hs, ws, symmetric, out=(warp, cert))
+        sf_hi = math.sqrt(self.upsample_res[0] * self.upsample_res[1] / (560 ** 2))
+        self.engine.run_match(images, images_hi, b, symmetric, scale_factor, sf_hi, attenuate, warp, cert)
 
     def _match_device(self, a_t, b_t, a_h, b_h, b, symmetric, scale_factor):
         eng = self.engine

@@ -26,12 +26,20 @@ def bench(name, fn, flops, reps=5):
     print(f"{name:44s} {t*1e3:9.1f} us  {flops/t/1e9:8.1f} TFLOP/s")
 
 
-def linear(M, N, K, **kw):
-    A = torch.randn(M, K, device=dev).to(dt); B = torch.randn(N, K, device=dev).to(dt)
-    C = torch.empty(M, N, device=dev, dtype=dt)
+def linear(M, N, K, residual=False, **kw):
+    ldk = (K + 7) // 8 * 8
+    ldn = (N + 7) // 8 * 8
+    A = torch.randn(M, ldk, device=dev).to(dt); B = torch.randn(N, ldk, device=dev).to(dt)
     bias = torch.randn(N, device=dev)
-    args = dict(A=A, B=B, C=C, M=M, N=N, K=K, lda=K, ldb=K, ldc=N, dtype_ab=CODE[dt], dtype_c=CODE[dt], batch0=1, batch1=1, ntaps=1,
-                alpha=1.0, bias=bias)
+    if residual:
+        C = torch.randn(M, ldn, device=dev)
+        gamma = torch.rand(N, device=dev)
+        args = dict(A=A, B=B, C=C, M=M, N=N, K=K, lda=ldk, ldb=ldk, ldc=ldn, dtype_ab=CODE[dt], dtype_c=cabi.RB_F32, batch0=1, batch1=1,
+                    ntaps=1, alpha=1.0, bias=bias, col_scale=gamma, R=C, ldr=ldn, dtype_r=cabi.RB_F32)
+    else:
+        C = torch.empty(M, ldn, device=dev, dtype=dt)
+        args = dict(A=A, B=B, C=C, M=M, N=N, K=K, lda=ldk, ldb=ldk, ldc=ldn, dtype_ab=CODE[dt], dtype_c=CODE[dt], batch0=1, batch1=1, ntaps=1,
+                    alpha=1.0, bias=bias)
     args.update(kw)
     return lambda: call("romab200_gemm", "rb_gemm_args", **args)
 
@@ -68,6 +76,13 @@ if which in ("all", "qkv"):
     bench("big      8192x8192x8192", linear(8192, 8192, 8192), 2 * 8192 ** 3)
     bench("ref8 pw  23328x1137x1137(pad1144)", linear(23328, 1137, 1144), 2 * 23328 * 1137 * 1137)
     bench("ref1 pw  1492992x24x24", linear(1492992, 24, 24), 2 * 1492992 * 24 * 24)
+if which in ("all", "ref"):
+    bench("ref2 pw  373248x144x144", linear(373248, 144, 144), 2 * 373248 * 144 * 144)
+    bench("ref4 pw  93312x569x569", linear(93312, 569, 569), 2 * 93312 * 569 * 569)
+    bench("ref8 pw  23328x1137x1137", linear(23328, 1137, 1137), 2 * 23328 * 1137 * 1137)
+    bench("vit proj+res 3202x1024x1024 f32 inplace", linear(3202, 1024, 1024, residual=True), 2 * 3202 * 1024 * 1024)
+if which in ("ref2",):
+    bench("ref2 pw  373248x144x144", linear(373248, 144, 144), 2 * 373248 * 144 * 144)
 if which in ("all", "attn"):
     f, keep = attn_qk(2, 16, 1601, 64)
     bench("vit QK^T 2x16x1601x1601x64", f, 2 * 32 * 1601 * 1601 * 64)

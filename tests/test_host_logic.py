@@ -105,7 +105,8 @@ def test_engine_dry_run(weights, monkeypatch, symmetric, upsample):
     eng.device = torch.device("cpu")
     eng.precision, eng.dtype, eng.dt = "fp32", torch.float32, cabi.RB_F32
     eng.w = PackedWeights(weights[0], weights[1], eng.device, torch.float32)
-    eng._buf, eng._const, eng.debug, eng.profile, eng.gemm_profile, eng.use_flash_attn = {}, {}, None, None, None, True
+    eng._buf, eng._const, eng.debug, eng.profile, eng.gemm_profile, eng.use_flash_attn, eng.gp_persistent = {}, {}, None, None, None, True, True
+    eng.overlap_cnn, eng._side, eng.gp_tensor_core = False, None, True
     for t in _tensors(eng.w):
         rec.track(t)
     orig_buf, orig_const = eng.buf, eng.const

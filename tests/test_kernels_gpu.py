@@ -194,8 +194,9 @@ def test_conv_first_and_maxpool():
 
 
 # ----------------------------------------------------------------------------------------------- GP solve
-@pytest.mark.parametrize("n,nrhs,batch", [(64, 40, 2), (100, 512, 1), (1600, 512, 2)])
-def test_gp_solve(n, nrhs, batch):
+@pytest.mark.parametrize("persistent", [False, True])
+@pytest.mark.parametrize("n,nrhs,batch", [(64, 40, 2), (100, 512, 1), (1600, 512, 2), (224, 70, 3)])
+def test_gp_solve(n, nrhs, batch, persistent):
     g = torch.Generator().manual_seed(n)
     feats = torch.randn(batch, n, 48, generator=g)
     feats = feats / feats.norm(dim=-1, keepdim=True)
@@ -207,13 +208,17 @@ def test_gp_solve(n, nrhs, batch):
     Wk[:, :n, :n] = Kyy
     Wk[:, n:, :n] = Fm.t()
     Wk = Wk.to(DEV)
-    call("romab200_gp_solve", "rb_gp_solve_args", W=Wk, n=n, nrhs=nrhs, batch=batch, ldw=ldw, stride=(n + nrhs) * ldw)
+    ws_floats = batch * ((n + 31) // 32) * 1024 + 1
+    ws = torch.empty(ws_floats, device=DEV)
+    call("romab200_gp_solve", "rb_gp_solve_args", W=Wk, n=n, nrhs=nrhs, batch=batch, ldw=ldw, stride=(n + nrhs) * ldw,
+         workspace=ws if persistent else None, workspace_bytes=ws_floats * 4 if persistent else 0)
+    torch.cuda.synchronize()
     alpha_t = Wk[:, n:, :n].cpu()
     err = (alpha_t.transpose(1, 2).double() - ref).abs().max().item()
     assert err < 5e-4 * ref.abs().max().item(), err
-    # lower triangle now holds the Cholesky factor
-    L = torch.tril(Wk[:, :n, :n].cpu().double())
-    close((L @ L.transpose(1, 2)).float(), Kyy, 1e-5)
+    if not persistent:       # in-place variant: the lower triangle now holds the Cholesky factor
+        L = torch.tril(Wk[:, :n, :n].cpu().double())
+        close((L @ L.transpose(1, 2)).float(), Kyy, 1e-5)
 
 
 # ----------------------------------------------------------------------------------------------- decoder pieces
