@@ -27,8 +27,9 @@ __global__ void __launch_bounds__(128) kde_kernel(const float* __restrict__ x, f
     for (int j0 = 0; j0 < n; j0 += 512) {
         for (int t = threadIdx.x; t < 512; t += 128) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            float nv = 0.f;
+            float nv = half ? INFINITY : 0.f;
             if (j0 + t < n) {
+                nv = 0.f;
                 v = reinterpret_cast<const float4*>(x)[j0 + t];
                 if (half) {
                     v.x = rh(v.x); v.y = rh(v.y); v.z = rh(v.z); v.w = rh(v.w);
@@ -39,21 +40,35 @@ __global__ void __launch_bounds__(128) kde_kernel(const float* __restrict__ x, f
         }
         __syncthreads();
         int lim = min(512, n - j0);
-        for (int t = 0; t < lim; ++t) {
-            float4 v = pts[t];
-            float e;
-            if (half) {
-                float s = ax * v.x;
-                s = fmaf(ay, v.y, s); s = fmaf(az, v.z, s); s = fmaf(aw, v.w, s);
-                s += ni; s += nrm[t];
-                float d = rh(sqrtf(fmaxf(rh(s), 0.f)));
-                float q = rh(-rh(d * d) / two_var);
-                e = rh(expf(q));
-            } else {
-                float dx = xi.x - v.x, dy = xi.y - v.y, dz = xi.z - v.z, dw = xi.w - v.w;
-                e = expf(-(dx * dx + dy * dy + dz * dz + dw * dw) / two_var);
+        if (half) {
+            // two pairs per iteration on packed fp16 pipes: fp32 dot product (the matmul), then the fp16 elementwise chain
+            // sqrt -> square -> scale -> exp with round-to-nearest at every step (h2sqrt / hmul2 / h2exp), fp32 row sum.
+            // padding entries (j >= n) hold x = 0, norm = +inf  ->  d = inf  ->  exp(-inf) = 0
+            const __half2 zero2 = __float2half2_rn(0.f);
+            const __half2 nscale = __float2half2_rn(-1.0f / two_var);
+            float acc2 = 0.f;
+#pragma unroll 4
+            for (int t = 0; t < 512; t += 2) {
+                if (t >= lim) break;
+                const float4 v0 = pts[t], v1 = pts[t + 1];
+                float s0 = ax * v0.x, s1 = ax * v1.x;
+                s0 = fmaf(ay, v0.y, s0); s1 = fmaf(ay, v1.y, s1);
+                s0 = fmaf(az, v0.z, s0); s1 = fmaf(az, v1.z, s1);
+                s0 = fmaf(aw, v0.w, s0); s1 = fmaf(aw, v1.w, s1);
+                s0 = (s0 + ni) + nrm[t]; s1 = (s1 + ni) + nrm[t + 1];
+                __half2 h = __hmax2(__floats2half2_rn(s0, s1), zero2);
+                const __half2 d = h2sqrt(h);
+                const __half2 q = __hmul2(__hmul2(d, d), nscale);
+                const float2 e = __half22float2(h2exp(q));
+                acc += e.x; acc2 += e.y;
             }
-            acc += e;
+            acc += acc2;
+        } else {
+            for (int t = 0; t < lim; ++t) {
+                float4 v = pts[t];
+                float dx = xi.x - v.x, dy = xi.y - v.y, dz = xi.z - v.z, dw = xi.w - v.w;
+                acc += expf(-(dx * dx + dy * dy + dz * dz + dw * dw) / two_var);
+            }
         }
         __syncthreads();
     }
