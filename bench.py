@@ -82,7 +82,10 @@ def cpu_reference_time(steps, warmup, budget_s=240.0, with_sample=True):
     import torch
     from oracle.roma_oracle import RomaOracle
     from roma_b200 import synthetic
-    torch.set_num_threads(os.cpu_count() or 1)
+    # measured on the 128-core GPU box (scripts/cpu_threads_probe.py): 16 thr 40 s, 32 thr 28 s, 64 thr 32 s, 128 thr 59 s for
+    # the coarse pass -> the oracle (like the reference: torch CPU ops) is fastest at ~32 threads; more only add contention
+    threads = int(os.environ.get("ROMA_CPU_THREADS", "0")) or min(os.cpu_count() or 1, 32)
+    torch.set_num_threads(threads)
     mw, dw = synthetic.make_weights(0)
     orc = RomaOracle(mw, dw, COARSE, UPSAMPLE)
     if warmup > 0:                                   # warm the thread pool / allocator on a tiny problem
@@ -138,6 +141,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keeps stdout to the single JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     amp = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.precision]
     mw, dw = synthetic.make_weights(0)
@@ -241,7 +246,11 @@ def run_ours(args):
             fl, t_ms, n = by[dom]
             ach = fl / (t_ms / 1e3) / 1e12
             roofline = {"kernel": f"romab200_gemm[{dom}]", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"],
-                        "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                        "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
+                        # dram__bytes_read+write of one representative launch (ViT fc1 3202x4096x1024 fp16, algorithmic bytes
+                        # 41.2 MB of which the 26 MB output stays in L2) from `ncu --set full`: profiles/r01_ncu_gemm_fc1.txt
+                        "traffic": 15090688 if dom == "tcgen05" else None,
+                        "traffic_launch": "vit fc1 3202x4096x1024 (profiles/r01_ncu_gemm_fc1.txt)" if dom == "tcgen05" else None,
                         "peak_source": peaks["source"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
                         "launches_timed": n, "share_of_step": t_ms / sum(ms_prof),
                         "measured_in": "second timed region of the same K steps, eager launches (per-kernel events cannot be read "

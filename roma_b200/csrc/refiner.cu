@@ -433,13 +433,12 @@ __global__ void __launch_bounds__(256) refiner_block_small_kernel(const T* __res
     constexpr int MS = C + 1;                 // mid pixel stride in floats
     __shared__ __align__(16) T tile[IN * IN * PS];
     __shared__ float mid[TS * TS * MS];
-    __shared__ __align__(16) float wpw[C * C];
-    __shared__ float bpw[C];
+    __shared__ __align__(16) float2 wpw[C * CP];      // [ci][co pair] = (W[2p][ci], W[2p+1][ci]): operands of the packed FFMA2
+    __shared__ float2 bpw[CP];
     const int tid = threadIdx.x;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, b = blockIdx.y;
     const int x0 = tx * TS, y0 = ty * TS;
     const T* inb = in + (int64_t)b * H * W * ld;
-    // ---- stage the (TS+4)^2 x C input tile (zero outside the image) and the pointwise weights
     {   // 16-byte global loads, all issued before the first shared store
         constexpr int VPP = C / 8, NV = IN * IN * VPP, PER = (NV + 255) / 256;
         uint4 vals[PER];
@@ -463,90 +462,111 @@ __global__ void __launch_bounds__(256) refiner_block_small_kernel(const T* __res
             }
         }
     }
-    for (int i = tid; i < C * C; i += 256) wpw[i] = pw_w[i];
-    if (tid < C) bpw[tid] = pw_b[tid];
-    // ---- depthwise: thread = (channel pair, output row)
+    for (int i = tid; i < C * CP; i += 256) {
+        const int ci = i / CP, pr = i - ci * CP;
+        wpw[i] = make_float2(pw_w[(2 * pr) * C + ci], pw_w[(2 * pr + 1) * C + ci]);
+    }
+    if (tid < CP) bpw[tid] = make_float2(pw_b[2 * tid], pw_b[2 * tid + 1]);
+    // ---- depthwise: thread = (channel pair, output row); taps in registers, packed FFMA2
     const int cp = tid % CP, row = tid / CP;
-    float w0[25], w1[25];
-    float b0 = 0.f, b1 = 0.f;
+    float2 wv[25];
+    float2 bv = make_float2(0.f, 0.f);
     if (row < TS) {
 #pragma unroll
-        for (int t = 0; t < 25; ++t) { w0[t] = dw_w[(int64_t)t * ldw + 2 * cp]; w1[t] = dw_w[(int64_t)t * ldw + 2 * cp + 1]; }
-        b0 = dw_b[2 * cp]; b1 = dw_b[2 * cp + 1];
+        for (int t = 0; t < 25; ++t) wv[t] = make_float2(dw_w[(int64_t)t * ldw + 2 * cp], dw_w[(int64_t)t * ldw + 2 * cp + 1]);
+        bv = make_float2(dw_b[2 * cp], dw_b[2 * cp + 1]);
     }
     __syncthreads();
     if (row < TS) {
-        float a0[TS], a1[TS];
+        float2 acc[TS];
 #pragma unroll
-        for (int i = 0; i < TS; ++i) { a0[i] = b0; a1[i] = b1; }
+        for (int i = 0; i < TS; ++i) acc[i] = bv;
 #pragma unroll
         for (int ky = 0; ky < 5; ++ky) {
 #pragma unroll
             for (int px = 0; px < IN; ++px) {
                 T pr[2];
                 *reinterpret_cast<uint32_t*>(pr) = *reinterpret_cast<const uint32_t*>(&tile[((row + ky) * IN + px) * PS + 2 * cp]);
-                const float v0 = to_f(pr[0]), v1 = to_f(pr[1]);
+                const float2 v = make_float2(to_f(pr[0]), to_f(pr[1]));
 #pragma unroll
                 for (int kx = 0; kx < 5; ++kx) {
                     const int ox = px - kx;
-                    if (ox >= 0 && ox < TS) {
-                        a0[ox] = fmaf(w0[ky * 5 + kx], v0, a0[ox]);
-                        a1[ox] = fmaf(w1[ky * 5 + kx], v1, a1[ox]);
-                    }
+                    if (ox >= 0 && ox < TS) acc[ox] = __ffma2_rn(wv[ky * 5 + kx], v, acc[ox]);
                 }
             }
         }
 #pragma unroll
         for (int i = 0; i < TS; ++i) {
             // the unfused path stores this activation in the 16-bit compute dtype: round identically
-            mid[(row * TS + i) * MS + 2 * cp] = to_f(from_f<T>(fmaxf(a0[i], 0.f)));
-            mid[(row * TS + i) * MS + 2 * cp + 1] = to_f(from_f<T>(fmaxf(a1[i], 0.f)));
+            mid[(row * TS + i) * MS + 2 * cp] = to_f(from_f<T>(fmaxf(acc[i].x, 0.f)));
+            mid[(row * TS + i) * MS + 2 * cp + 1] = to_f(from_f<T>(fmaxf(acc[i].y, 0.f)));
         }
     }
     __syncthreads();
-    // ---- pointwise: thread = pixel
+    // ---- pointwise: thread = pixel, two output channels per FFMA2 against broadcast weights
     const int py = tid / TS, px = tid - py * TS;
     const int yy = y0 + py, xx = x0 + px;
     if (yy >= H || xx >= W) return;
-    float a[C];
+    float2 o[CP];
 #pragma unroll
-    for (int c = 0; c < C; ++c) a[c] = mid[tid * MS + c];
-    T* o = out + ((int64_t)b * H * W + (int64_t)yy * W + xx) * ld;
+    for (int pr = 0; pr < CP; ++pr) o[pr] = bpw[pr];
 #pragma unroll
-    for (int co = 0; co < C; co += 2) {
-        float s0 = bpw[co], s1 = bpw[co + 1];
+    for (int ci = 0; ci < C; ++ci) {
+        const float av = mid[tid * MS + ci];
+        const float2 a2 = make_float2(av, av);
 #pragma unroll
-        for (int ci = 0; ci < C; ci += 4) {
-            const float4 wa = *reinterpret_cast<const float4*>(&wpw[co * C + ci]);
-            const float4 wb = *reinterpret_cast<const float4*>(&wpw[(co + 1) * C + ci]);
-            s0 = fmaf(wa.x, a[ci], s0); s0 = fmaf(wa.y, a[ci + 1], s0); s0 = fmaf(wa.z, a[ci + 2], s0); s0 = fmaf(wa.w, a[ci + 3], s0);
-            s1 = fmaf(wb.x, a[ci], s1); s1 = fmaf(wb.y, a[ci + 1], s1); s1 = fmaf(wb.z, a[ci + 2], s1); s1 = fmaf(wb.w, a[ci + 3], s1);
+        for (int pr = 0; pr < CP; pr += 2) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&wpw[ci * CP + pr]);     // two channel pairs per LDS.128
+            o[pr] = __ffma2_rn(make_float2(w4.x, w4.y), a2, o[pr]);
+            o[pr + 1] = __ffma2_rn(make_float2(w4.z, w4.w), a2, o[pr + 1]);
         }
-        T pair[2] = {from_f<T>(s0), from_f<T>(s1)};
-        *reinterpret_cast<uint32_t*>(o + co) = *reinterpret_cast<uint32_t*>(pair);
     }
+    T* op = out + ((int64_t)b * H * W + (int64_t)yy * W + xx) * ld;
+    T res[C];
+#pragma unroll
+    for (int pr = 0; pr < CP; ++pr) { res[2 * pr] = from_f<T>(o[pr].x); res[2 * pr + 1] = from_f<T>(o[pr].y); }
+#pragma unroll
+    for (int v = 0; v < C / 8; ++v) *reinterpret_cast<uint4*>(op + 8 * v) = *reinterpret_cast<const uint4*>(&res[8 * v]);
 }
 
 // --------------------------------------------------------------------------------------------------
 // out_conv (C -> 3, fp32) + state update: one warp per pixel
 // --------------------------------------------------------------------------------------------------
-template <typename T>
+// LPP lanes cooperate on one pixel (32 for the wide maps, 8 / 4 for the thin ones so that no lane idles on 1.5 M pixels);
+// every lane reads 16-byte channel vectors, partial dot products are combined with shuffles inside the lane group.
+template <typename T, int LPP>
 __global__ void __launch_bounds__(256) refiner_tail_kernel(const T* __restrict__ d, int64_t ldd, const float* __restrict__ wgt, int64_t ldw,
                                                            const float* __restrict__ bias, float* __restrict__ state, int64_t rows, int C,
                                                            float sx, float sy, float* __restrict__ delta_out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const T* dr = d + row * ldd;
+    constexpr int VN = Vec16<T>::N;
+    const int sub = threadIdx.x % LPP;
+    const int64_t row = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPP;
+    const bool live = row < rows;
+    const int cpad = (C + VN - 1) / VN * VN;              // weights and activations are zero-padded to the vector width
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int c = lane; c < C; c += 32) {
-        float v = to_f(dr[c]);
-        a0 = fmaf(v, wgt[c], a0);
-        a1 = fmaf(v, wgt[ldw + c], a1);
-        a2 = fmaf(v, wgt[2 * ldw + c], a2);
+    if (live) {
+        const T* dr = d + row * ldd;
+        for (int c = sub * VN; c < cpad; c += LPP * VN) {
+            float v[VN];
+            load_vec<T>(dr + c, v);
+#pragma unroll
+            for (int e = 0; e < VN; e += 4) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wgt + c + e);
+                const float4 w1 = *reinterpret_cast<const float4*>(wgt + ldw + c + e);
+                const float4 w2 = *reinterpret_cast<const float4*>(wgt + 2 * ldw + c + e);
+                a0 += v[e] * w0.x + v[e + 1] * w0.y + v[e + 2] * w0.z + v[e + 3] * w0.w;
+                a1 += v[e] * w1.x + v[e + 1] * w1.y + v[e + 2] * w1.z + v[e + 3] * w1.w;
+                a2 += v[e] * w2.x + v[e + 1] * w2.y + v[e + 2] * w2.z + v[e + 3] * w2.w;
+            }
+        }
     }
-    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-    if (lane == 0) {
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (live && sub == 0) {
         a0 += bias[0]; a1 += bias[1]; a2 += bias[2];
         if (delta_out) { delta_out[row * 3 + 0] = a0; delta_out[row * 3 + 1] = a1; delta_out[row * 3 + 2] = a2; }
         state[row * 3 + 0] += sx * a0;
@@ -765,7 +785,7 @@ extern "C" int romab200_refiner_block_small(const rb_refiner_block_small_args* a
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->c == 24, "refiner_block_small: only C = 24 is instantiated (got %d)", a->c);
     RB_REQUIRE(a->dtype == RB_F16 || a->dtype == RB_BF16, "refiner_block_small: 16-bit activations only");
-    RB_REQUIRE(a->ld % 8 == 0 && ((uintptr_t)a->in) % 16 == 0 && ((uintptr_t)a->out) % 4 == 0 && a->in != a->out, "refiner_block_small: bad layout");
+    RB_REQUIRE(a->ld % 8 == 0 && ((uintptr_t)a->in) % 16 == 0 && ((uintptr_t)a->out) % 16 == 0 && a->in != a->out, "refiner_block_small: bad layout");
     int tiles_x = (a->w + 15) / 16, tiles_y = (a->h + 15) / 16;
     dim3 grid(tiles_x * tiles_y, a->batch);
     RB_REQUIRE(grid.y <= 65535, "refiner_block_small: batch too large");
@@ -780,10 +800,18 @@ extern "C" int romab200_refiner_block_small(const rb_refiner_block_small_args* a
 
 extern "C" int romab200_refiner_tail(const rb_refiner_tail_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned grid = (unsigned)((a->rows + 7) / 8);
-    if (a->dtype == RB_F32) refiner_tail_kernel<float><<<grid, 256, 0, st>>>((const float*)a->d, a->ldd, a->weight, a->ldw, a->bias, a->state, a->rows, a->c, a->scale_x, a->scale_y, a->delta_out);
-    else if (a->dtype == RB_F16) refiner_tail_kernel<__half><<<grid, 256, 0, st>>>((const __half*)a->d, a->ldd, a->weight, a->ldw, a->bias, a->state, a->rows, a->c, a->scale_x, a->scale_y, a->delta_out);
-    else refiner_tail_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->d, a->ldd, a->weight, a->ldw, a->bias, a->state, a->rows, a->c, a->scale_x, a->scale_y, a->delta_out);
+    const int vn = a->dtype == RB_F32 ? 4 : 8;
+    const int cpad = (a->c + vn - 1) / vn * vn;
+    RB_REQUIRE(a->ldd >= cpad && a->ldw >= cpad && a->ldd % vn == 0 && a->ldw % 4 == 0 && ((uintptr_t)a->d) % 16 == 0 &&
+               ((uintptr_t)a->weight) % 16 == 0, "refiner_tail: rows must be zero-padded to whole 16-byte vectors (c=%d ldd=%lld ldw=%lld)",
+               a->c, (long long)a->ldd, (long long)a->ldw);
+    const int lpp = a->c <= 32 ? 4 : (a->c <= 256 ? 8 : 32);
+    unsigned grid = (unsigned)((a->rows * lpp + 255) / 256);
+#define TAIL(T, L) refiner_tail_kernel<T, L><<<grid, 256, 0, st>>>((const T*)a->d, a->ldd, a->weight, a->ldw, a->bias, a->state, a->rows, a->c, a->scale_x, a->scale_y, a->delta_out)
+#define BYL(T) if (lpp == 4) TAIL(T, 4); else if (lpp == 8) TAIL(T, 8); else TAIL(T, 32);
+    if (a->dtype == RB_F32) { BYL(float) } else if (a->dtype == RB_F16) { BYL(__half) } else { BYL(__nv_bfloat16) }
+#undef BYL
+#undef TAIL
     return check_launch("refiner_tail");
 }
 
