@@ -125,15 +125,15 @@ constexpr int TC_BM = 128, TC_BK = 64;
 template <int BN> struct TcCfg {
     // BN = 256: one CTA per SM with 8 epilogue warps; narrower tiles: two CTAs per SM (two MMA-issuing threads keep the
     // tensor pipe fed when a k-block is only 128-256 MMA cycles) with 4 epilogue warps each
-    static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);
-    static constexpr int CTAS_PER_SM = BN >= 256 ? 1 : 2;
-    static constexpr int EPI_WARPS = BN >= 256 ? 8 : 4;
+    static constexpr int STAGES = BN >= 256 ? 4 : (BN > 128 ? 5 : (BN >= 128 ? 3 : 4));
+    static constexpr int CTAS_PER_SM = BN > 128 ? 1 : 2;
+    static constexpr int EPI_WARPS = BN > 128 ? 8 : 4;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int EPI_BYTES = 2 * 256 * 4;                        // staged bias / column-scale (or norm_b) of the tile
     static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // two accumulator stages
+    static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));   // two accumulator stages
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -267,17 +267,18 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __
             asm volatile("bar.sync 1, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");
             mbar_wait(&tmem_full_bar[acc], acc_ph);
             tc_fence_after();
+            const int nlim = min(p.N, n0 + BN);                  // columns of this tile (BN need not be a multiple of 32)
             const int m = m0 + q * 32 + lane;
             const int64_t orow = m < p.M ? e.map_row(m) : -1;
             const bool vec_ok = (e.ldc * dtype_size(e.dtype_c)) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.C) % 16 == 0);
 #pragma unroll 1
             for (int cb = half * 32; cb < BN; cb += 8 * Cfg::EPI_WARPS) {
-                if (n0 + cb >= p.N) break;                     // warp-uniform
+                if (n0 + cb >= nlim) break;                     // warp-uniform
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cb, v);
                 if (orow < 0) continue;
                 const int nb = n0 + cb;
-                const bool full = nb + 32 <= p.N;
+                const bool full = nb + 32 <= nlim;
                 // every branch below is warp-uniform: the per-element work is straight-line code
                 if (e.epi == RB_EPI_COSKERNEL) {
                     const float na = e.norm_a[m];
@@ -319,13 +320,13 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __
                     if (e.R) {
                         if (e.dtype_r == RB_F32) {
                             float rv[32];
-                            load_row32((const float*)e.R + orow * e.ldr + nb, rv, full, p.N - nb);
+                            load_row32((const float*)e.R + orow * e.ldr + nb, rv, full, nlim - nb);
     #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] += rv[j];
                         } else {
     #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (nb + j < p.N) v[j] += load_any(e.R, orow * e.ldr + nb + j, e.dtype_r);
+                                if (nb + j < nlim) v[j] += load_any(e.R, orow * e.ldr + nb + j, e.dtype_r);
                         }
                     }
                 }
@@ -334,10 +335,10 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __
                         float* dst = (float*)e.C + orow * e.ldc + nb;
     #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            if (nb + 4 * j + 4 <= p.N) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            if (nb + 4 * j + 4 <= nlim) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                             else {
     #pragma unroll
-                                for (int t = 0; t < 4; ++t) if (nb + 4 * j + t < p.N) dst[4 * j + t] = v[4 * j + t];
+                                for (int t = 0; t < 4; ++t) if (nb + 4 * j + t < nlim) dst[4 * j + t] = v[4 * j + t];
                             }
                         }
                     } else {
@@ -351,18 +352,18 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __
                                 if (e.dtype_c == RB_F16) { __half2 h = __floats2half2_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
                                 else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
                             }
-                            if (nb + 8 * j + 8 <= p.N) *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+                            if (nb + 8 * j + 8 <= nlim) *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
                             else {
     #pragma unroll
                                 for (int t = 0; t < 8; ++t)
-                                    if (nb + 8 * j + t < p.N) dst[8 * j + t] = (uint16_t)(w[t >> 1] >> (16 * (t & 1)));
+                                    if (nb + 8 * j + t < nlim) dst[8 * j + t] = (uint16_t)(w[t >> 1] >> (16 * (t & 1)));
                             }
                         }
                     }
                 } else {
     #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (nb + j < p.N) store_any(e.C, orow * e.ldc + nb + j, e.dtype_c, v[j]);
+                        if (nb + j < nlim) store_any(e.C, orow * e.ldc + nb + j, e.dtype_c, v[j]);
                 }
             }
             tc_fence_before();
@@ -463,8 +464,17 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
     RB_REQUIRE(zdim <= 65535, "gemm_tc: batch too large");
     const int64_t a_rows = a->a_rows > 0 ? a->a_rows : a->M;
     int BN = a->N <= 32 && !a->trans_b ? 32 : (a->N <= 64 ? 64 : (a->N <= 128 || a->trans_b ? 128 : 256));
-    // very tall-skinny K: keep 128-wide tiles so that more CTAs are in flight
-    if (BN == 256 && ((int64_t)((a->M + 127) / 128) * ((a->N + 255) / 256) * zdim) < 148) BN = 128;
+    if (!a->trans_b && a->N > 128) {
+        // UMMA N may be any multiple of 16: pick the tile width that wastes the fewest columns (C = 144 / 569 / 1137 ...)
+        if (a->N <= 144) BN = 144;
+        else if (a->N <= 192) BN = 192;
+        else {
+            const int w192 = (a->N + 191) / 192 * 192 - a->N, w256 = (a->N + 255) / 256 * 256 - a->N;
+            BN = (w192 + a->N / 20 < w256) ? 192 : 256;
+        }
+    }
+    // few tiles: keep 128-wide tiles so that more CTAs are in flight
+    if (BN > 128 && ((int64_t)((a->M + 127) / 128) * ((a->N + BN - 1) / BN) * zdim) < 148) BN = 128;
     CUtensorMap ma, mb;
     if (make_map(&ma, a->A, p.is_bf16, p.ntaps > 1 ? p.k_per_tap : a->K, a_rows, a->lda, p.batch1, a->sa1, batch0, a->sa0, TC_BK, TC_BM)) return 1;
     if (!a->trans_b) {
@@ -476,6 +486,8 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
         case 32: return launch_tc<32>(ma, mb, p, zdim, stream);
         case 64: return launch_tc<64>(ma, mb, p, zdim, stream);
         case 128: return launch_tc<128>(ma, mb, p, zdim, stream);
+        case 144: return launch_tc<144>(ma, mb, p, zdim, stream);
+        case 192: return launch_tc<192>(ma, mb, p, zdim, stream);
         default: return launch_tc<256>(ma, mb, p, zdim, stream);
     }
 }

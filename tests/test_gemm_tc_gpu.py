@@ -32,7 +32,8 @@ def close(a, b, tol):
 
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 136), (1000, 24, 24), (257, 4097, 1024), (130, 64, 592), (3200, 1377, 1384), (500, 9, 64)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 136), (1000, 24, 24), (257, 4097, 1024), (130, 64, 592), (3200, 1377, 1384), (500, 9, 64),
+                                   (20000, 144, 144), (19000, 569, 569), (19000, 1137, 1137), (19000, 130, 72), (19000, 192, 200)])
 def test_tc_plain_f32_out(dt, M, N, K):
     lda = (K + 7) // 8 * 8
     A, B = rnd(M, lda, seed=1, dtype=dt), rnd(N, lda, seed=2, dtype=dt)
