@@ -202,6 +202,15 @@ typedef struct {
 } rb_refiner_block_small_args;
 int romab200_refiner_block_small(const rb_refiner_block_small_args* args, void* stream);
 
+/* Fused ConvRefiner block for the stride-2 maps (C = 144): depthwise 5x5 + BN + ReLU on the CUDA cores feeding a
+ * tcgen05 pointwise GEMM whose weights stay resident in shared memory; one read + one write of the map.
+ * in/out [batch, h, w, ld] 16-bit (in != out); dw_weight [25][ldw] fp32 (BN folded), pw_weight [144][ld_pw] 16-bit. */
+typedef struct {
+    const void* in; void* out; int64_t ld; const float* dw_weight; int64_t ldw; const float* dw_bias;
+    const void* pw_weight; int64_t ld_pw; const float* pw_bias; int32_t batch, h, w, c; int32_t dtype;
+} rb_refiner_block_c144_args;
+int romab200_refiner_block_c144(const rb_refiner_block_c144_args* args, void* stream);
+
 /* out_conv (fp32 1x1, C -> 3) + flow/certainty update (matcher.py:177-179, 496-506):
  * state[...,0] += scale_x * o0 ; state[...,1] += scale_y * o1 ; state[...,2] += o2 */
 typedef struct {

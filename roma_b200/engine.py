@@ -55,6 +55,7 @@ class Engine:
                                                  # faster than the launch chain, and cooperative launches do not overlap the CNN branch)
         self.overlap_cnn = True                  # VGG/proj branch on a side stream, overlapping ViT / GP / decoder
         self.gp_tensor_core = True               # all-pairs CosKernel on tcgen05 (split-fp16 operands) in the 16-bit modes
+        self.fused_c144 = True                   # stride-2 refiner blocks as one fused DW + tcgen05-PW kernel
         self._side = None
         self.profile: Optional[dict] = None      # set to {} to collect CUDA-event timings per stage (bench.py)
         self.gemm_profile: Optional[list] = None  # set to [] to time every GEMM launch: (backend, flops, start, end)
@@ -384,6 +385,12 @@ class Engine:
             for blk in R["blocks"]:
                 call("romab200_refiner_block_small", "rb_refiner_block_small_args", **{"in": d}, out=t, ld=cp, dw_weight=blk["dw_w"],
                      ldw=cp, dw_bias=blk["dw_b"], pw_weight=blk["pw_w32"], pw_bias=blk["pw_b"], batch=D, h=h, w=w, c=c, dtype=self.dt)
+                d, t = t, d
+        elif c == 144 and self.dtype != torch.float32 and self.fused_c144:
+            # stride-2 maps: depthwise stage on the CUDA cores feeding a tcgen05 pointwise GEMM inside one kernel
+            for blk in R["blocks"]:
+                call("romab200_refiner_block_c144", "rb_refiner_block_c144_args", **{"in": d}, out=t, ld=cp, dw_weight=blk["dw_w"], ldw=cp,
+                     dw_bias=blk["dw_b"], pw_weight=blk["pw_w"], ld_pw=cp, pw_bias=blk["pw_b"], batch=D, h=h, w=w, c=c, dtype=self.dt)
                 d, t = t, d
         else:
             for blk in R["blocks"]:

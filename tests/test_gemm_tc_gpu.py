@@ -162,3 +162,22 @@ def test_flash_attn(dt, H, d, N, Bn):
     q, k, v = qkv.float().reshape(Bn, N, 3, H, d).unbind(2)
     ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2).reshape(Bn, N, dim)
     close(out, ref, 2.5e-2 if dt == torch.bfloat16 else 4e-3)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W", [(2, 37, 50), (1, 8, 16), (2, 84, 84)])
+def test_refiner_block_c144_fused(dt, B, H, W):
+    """Fused stride-2 block (DW5x5+ReLU on CUDA cores -> tcgen05 PW 144x144) against conv2d on the same rounded tensors."""
+    C = 144
+    x = rnd(B, C, H, W, seed=1, dtype=dt)
+    dw, db = rnd(C, 1, 5, 5, seed=2, scale=0.3, dtype=torch.float32), rnd(C, seed=3, dtype=torch.float32)
+    pw, pb = rnd(C, C, seed=4, scale=0.1, dtype=dt), rnd(C, seed=5, dtype=torch.float32)
+    mid = F.relu(F.conv2d(x.float(), dw, db, padding=2, groups=C)).to(dt).float()
+    ref = (torch.einsum("bchw,oc->bohw", mid, pw.float()) + pb[None, :, None, None]).permute(0, 2, 3, 1)
+    xi = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.full((B, H, W, C), 7.0, dtype=dt, device=DEV)
+    dwt = dw.reshape(C, 25).t().contiguous()
+    call("romab200_refiner_block_c144", "rb_refiner_block_c144_args", **{"in": xi}, out=out, ld=C, dw_weight=dwt, ldw=C, dw_bias=db,
+         pw_weight=pw.contiguous(), ld_pw=C, pw_bias=pb, batch=B, h=H, w=W, c=C, dtype=CODE[dt])
+    torch.cuda.synchronize()
+    close(out, ref, 1.5e-1 if dt == torch.bfloat16 else 2e-2)
