@@ -148,7 +148,11 @@ int romab200_assemble_tokens(const rb_tokens_args* args, void* stream);
  * Replaces torch.linalg.cholesky + torch.cholesky_solve (matcher.py:307-308). */
 typedef struct {
     float* W; int32_t n, nrhs, batch; int64_t ldw, stride;
-    void* workspace; int64_t workspace_bytes;   /* optional: >= (batch*ceil(n/32)*1024 + 1)*4 bytes -> single persistent cooperative launch */
+    void* workspace; int64_t workspace_bytes;
+    int32_t algo;   /* 0: 32-wide panels, chain of small launches (no workspace)
+                       1: the same as ONE cooperative persistent kernel; workspace >= (batch*ceil(n/32)*1024 + 1)*4 bytes
+                       2: 128-wide blocks factored in shared memory with explicit block inverses, all O(n^2) work as K=128
+                          GEMMs; workspace >= batch*ceil(n/128)*65536 bytes (receives the diagonal-block inverses) */
 } rb_gp_solve_args;
 int romab200_gp_solve(const rb_gp_solve_args* args, void* stream);
 /* ---- classifier head -> coarse flow (utils.py:300-322) ------------------------------------------

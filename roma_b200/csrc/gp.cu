@@ -348,6 +348,185 @@ static int sub_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, in
     return gemm_simt(&g, st);
 }
 
+
+// --------------------------------------------------------------------------------------------------
+// 128-wide blocked variant (algo 2): the dependent chain shrinks from n/32 = 50 to n/128 = 13 steps and every O(n^2)
+// piece becomes a K = 128 GEMM.  One CTA per problem factors the 128x128 diagonal block entirely in shared memory
+// (four 32-wide sub-panels) and also forms its explicit inverse, so that the panel solve  P = A21 L11^-T  and the
+// backward block solve  X = Y L11^-1  are plain GEMMs against the inverse (diagonal blocks of K + sigma*I are well
+// conditioned: cond(L11) <= ~30).
+// --------------------------------------------------------------------------------------------------
+constexpr int BB = 128, BBP = BB + 1;
+
+__device__ __forceinline__ void mm32_acc(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float acc[4], int r, int c4) {
+    // acc[0..3] += A[r, 0:32] . B[0:32, c4*4 .. c4*4+3]   (32x32 blocks in shared memory)
+#pragma unroll 8
+    for (int p = 0; p < 32; ++p) {
+        const float a = A[r * lda + p];
+        const float* b = B + p * ldb + c4 * 4;
+        acc[0] = fmaf(a, b[0], acc[0]); acc[1] = fmaf(a, b[1], acc[1]); acc[2] = fmaf(a, b[2], acc[2]); acc[3] = fmaf(a, b[3], acc[3]);
+    }
+}
+
+__global__ void __launch_bounds__(256) chol_block128_kernel(float* __restrict__ W, float* __restrict__ inv_ws, int64_t ldw, int64_t stride,
+                                                            int64_t ws_stride, int k, int kb, int bs) {
+    extern __shared__ float sm128[];
+    float (*S)[BBP] = reinterpret_cast<float (*)[BBP]>(sm128);                    // the block, then its factor L
+    float (*V)[BBP] = reinterpret_cast<float (*)[BBP]>(sm128 + BB * BBP);         // L^-1
+    float (*T)[33] = reinterpret_cast<float (*)[33]>(sm128 + 2 * BB * BBP);       // 32x32 scratch
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* Wd = W + (int64_t)blockIdx.x * stride + (int64_t)k * ldw + k;
+    for (int idx = tid; idx < BB * BB; idx += 256) {
+        const int i = idx >> 7, c = idx & 127;
+        float v = 0.f;
+        if (i < bs && c < bs && c <= i) v = __ldcg(Wd + (int64_t)i * ldw + c);
+        if (i == c && i >= bs) v = 1.f;                       // identity padding of a partial block
+        S[i][c] = v; V[i][c] = 0.f;
+    }
+    __syncthreads();
+    // ---- factorisation: four 32-wide sub-panels, everything in shared memory
+    for (int jb = 0; jb < 4; ++jb) {
+        const int j0 = 32 * jb;
+        if (warp == 0) {                                      // 32x32 diagonal sub-block, one row per lane (shuffles)
+            float r[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) r[c] = c <= lane ? S[j0 + lane][j0 + c] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float d = sqrtf(__shfl_sync(0xffffffffu, r[j], j));
+                float lij = 0.f;
+                if (lane == j) r[j] = d;
+                else if (lane > j) { lij = r[j] / d; r[j] = lij; }
+#pragma unroll
+                for (int c = j + 1; c < 32; ++c) {
+                    const float lcj = __shfl_sync(0xffffffffu, lij, c);
+                    if (c <= lane) r[c] = fmaf(-lij, lcj, r[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) S[j0 + lane][j0 + c] = c <= lane ? r[c] : 0.f;
+        }
+        __syncthreads();
+        const int row = j0 + 32 + tid;                        // rows of the block below the sub-panel
+        if (tid < 96 && row < BB) {
+            float a[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) a[c] = S[row][j0 + c];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float x = a[j] / S[j0 + j][j0 + j];
+                a[j] = x;
+#pragma unroll
+                for (int c = j + 1; c < 32; ++c) a[c] = fmaf(-x, S[j0 + c][j0 + j], a[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) S[row][j0 + c] = a[c];
+        }
+        __syncthreads();
+        const int rem = BB - (j0 + 32);                       // trailing part of the block: lower triangle only
+        for (int idx = tid; idx < rem * rem; idx += 256) {
+            const int i = j0 + 32 + idx / rem, c = j0 + 32 + idx % rem;
+            if (c <= i) {
+                float s = 0.f;
+#pragma unroll 8
+                for (int p = 0; p < 32; ++p) s = fmaf(S[i][j0 + p], S[c][j0 + p], s);
+                S[i][c] -= s;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- inverse of the lower-triangular factor, block-wise: V_bb = L_bb^-1, V_ij = -V_ii (sum_m L_im V_mj)
+    if (tid < 128) {
+        const int b = tid >> 5, j = tid & 31, o = 32 * b;
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float s = i == j ? 1.f : 0.f;
+#pragma unroll
+            for (int p = 0; p < 32; ++p)
+                if (p < i) s = fmaf(-S[o + i][o + p], x[p], s);
+            x[i] = i >= j ? s / S[o + i][o + i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) V[o + i][o + j] = x[i];
+    }
+    __syncthreads();
+    const int r = tid >> 3, c4 = tid & 7;
+    for (int d = 1; d < 4; ++d) {
+        for (int bi = d; bi < 4; ++bi) {
+            const int bj = bi - d;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int m = bj; m < bi; ++m) mm32_acc(&S[32 * bi][32 * m], BBP, &V[32 * m][32 * bj], BBP, acc, r, c4);
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) T[r][c4 * 4 + q] = acc[q];
+            __syncthreads();
+            float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+            mm32_acc(&V[32 * bi][32 * bi], BBP, &T[0][0], 33, acc2, r, c4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) V[32 * bi + r][32 * bj + c4 * 4 + q] = -acc2[q];
+            __syncthreads();
+        }
+    }
+    // ---- write back: L in place (lower triangle), L^-1 to the workspace as a dense [128][128] block
+    float* Vout = inv_ws + (int64_t)blockIdx.x * ws_stride + (int64_t)kb * BB * BB;
+    for (int idx = tid; idx < BB * BB; idx += 256) {
+        const int i = idx >> 7, c = idx & 127;
+        if (i < bs && c < bs && c <= i) Wd[(int64_t)i * ldw + c] = S[i][c];
+        Vout[idx] = V[i][c];
+    }
+}
+
+static int plain_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int trans_b, float* C, int64_t ldc, int M, int N, int K,
+                      int batch, int64_t sa, int64_t sb, int64_t sc, cudaStream_t st) {
+    rb_gemm_args g = {};
+    g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    g.dtype_ab = RB_F32; g.dtype_c = RB_F32; g.trans_b = trans_b;
+    g.batch0 = batch; g.batch1 = 1; g.sa0 = sa; g.sb0 = sb; g.sc0 = sc;
+    g.ntaps = 1; g.alpha = 1.0f;
+    return gemm_simt(&g, st);
+}
+
+static int gp_solve_block128(const rb_gp_solve_args* a, cudaStream_t st) {
+    const int n = a->n, total = a->n + a->nrhs, nblk = (n + BB - 1) / BB;
+    const int64_t ws_stride = (int64_t)nblk * BB * BB;
+    float* W = a->W;
+    float* ws = (float*)a->workspace;
+    static bool configured = false;
+    const size_t smem = (size_t)(2 * BB * BBP + 32 * 33) * sizeof(float);
+    if (!configured) {
+        RB_REQUIRE(cudaFuncSetAttribute(chol_block128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
+                   "gp_solve: cannot reserve %zu bytes of shared memory", smem);
+        configured = true;
+    }
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k = kb * BB, bs = n - k < BB ? n - k : BB;
+        chol_block128_kernel<<<a->batch, 256, smem, st>>>(W, ws, a->ldw, a->stride, ws_stride, k, kb, bs);
+        if (check_launch("chol_block128")) return 1;
+        const int below = total - (k + bs);
+        if (below > 0) {
+            float* P = W + (int64_t)(k + bs) * a->ldw + k;                 // A21 (and the F^T rows)  ->  P = A21 L11^-T, in place
+            if (plain_gemm(P, a->ldw, ws + (int64_t)kb * BB * BB, BB, 0, P, a->ldw, below, bs, bs, a->batch, a->stride, ws_stride, a->stride, st)) return 1;
+            const int nt = n - (k + bs);
+            if (nt > 0) {
+                float* Tm = W + (int64_t)(k + bs) * a->ldw + (k + bs);
+                if (sub_gemm(P, a->ldw, P, a->ldw, 0, Tm, a->ldw, below, nt, bs, a->batch, a->stride, st)) return 1;
+            }
+        }
+    }
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int k = kb * BB, bs = n - k < BB ? n - k : BB;
+        float* Y = W + (int64_t)n * a->ldw + k;                            // RHS block  ->  X = Y L11^-1, in place
+        if (plain_gemm(Y, a->ldw, ws + (int64_t)kb * BB * BB, BB, 1, Y, a->ldw, a->nrhs, bs, bs, a->batch, a->stride, ws_stride, a->stride, st)) return 1;
+        if (k > 0) {
+            float* Lr = W + (int64_t)k * a->ldw;
+            float* Y0 = W + (int64_t)n * a->ldw;
+            if (sub_gemm(Y, a->ldw, Lr, a->ldw, 1, Y0, a->ldw, a->nrhs, k, bs, a->batch, a->stride, st)) return 1;
+        }
+    }
+    return 0;
+}
+
 }  // namespace rb
 
 using namespace rb;
@@ -356,7 +535,13 @@ extern "C" int romab200_gp_solve(const rb_gp_solve_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->n > 0 && a->nrhs > 0 && a->batch > 0 && a->ldw >= a->n, "gp_solve: bad shape n=%d nrhs=%d batch=%d", a->n, a->nrhs, a->batch);
     RB_REQUIRE(a->batch <= 65535, "gp_solve: batch too large");
-    if (a->workspace) {
+    if (a->workspace && a->algo == 2) {
+        const int64_t nblk128 = (a->n + BB - 1) / BB;
+        RB_REQUIRE(a->ldw % 4 == 0 && ((uintptr_t)a->W) % 16 == 0 && ((uintptr_t)a->workspace) % 16 == 0, "gp_solve: alignment");
+        RB_REQUIRE(a->workspace_bytes >= (int64_t)a->batch * nblk128 * BB * BB * 4, "gp_solve: workspace too small for algo 2");
+        return gp_solve_block128(a, st);
+    }
+    if (a->workspace && a->algo == 1) {
         // single cooperative launch; workspace = [batch * ceil(n/32) * 1024 floats of diagonal factors | 1 counter word]
         RB_REQUIRE(a->ldw % 4 == 0 && ((uintptr_t)a->W) % 16 == 0, "gp_solve: W must be 16-byte aligned with ldw %% 4 == 0");
         const int64_t nblk = (a->n + NB - 1) / NB;

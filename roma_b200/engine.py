@@ -51,8 +51,9 @@ class Engine:
         self._const: Dict[tuple, torch.Tensor] = {}
         self.debug: Optional[dict] = None        # set to {} to keep stage tensors (tests)
         self.use_flash_attn = True               # fused tcgen05 attention in the 16-bit modes (else QK^T / softmax / PV GEMMs)
-        self.gp_persistent = False               # True: GP Cholesky + solves as one cooperative persistent kernel (measured: no
-                                                 # faster than the launch chain, and cooperative launches do not overlap the CNN branch)
+        self.gp_algo = 0                         # 0: 32-wide launch chain (fastest measured: 3.4 ms for two 1600^2 problems),
+                                                 # 1: one cooperative persistent kernel (4.0 ms), 2: 128-wide blocks factored in shared
+                                                 # memory + explicit block inverses (8.8 ms: the in-smem block kernel is latency-bound)
         self.overlap_cnn = True                  # VGG/proj branch on a side stream, overlapping ViT / GP / decoder
         self.gp_tensor_core = True               # all-pairs CosKernel on tcgen05 (split-fp16 operands) in the 16-bit modes
         self.fused_c144 = True                   # stride-2 refiner blocks as one fused DW + tcgen05-PW kernel
@@ -302,10 +303,11 @@ class Engine:
         for e in range(E):
             self.copy2d(basis_t, Wk.data_ptr() + (e * stride_w + n * ldw) * 4, nrhs, n, n, ldw, f32, f32)
         with self.stage("  gp.solve"):
-            ws_bytes = (E * ((n + 31) // 32) * 1024 + 1) * 4
+            # algo 2: 128-wide blocks factored in shared memory + explicit block inverses, everything else K=128 GEMMs
+            ws_bytes = max((E * ((n + 31) // 32) * 1024 + 1) * 4, E * ((n + 127) // 128) * 65536)
             ws = self.buf("gp.solve_ws", (ws_bytes // 4,), dtype=torch.float32)
             call("romab200_gp_solve", "rb_gp_solve_args", W=Wk, n=n, nrhs=nrhs, batch=E, ldw=ldw, stride=stride_w,
-                 workspace=ws if self.gp_persistent else None, workspace_bytes=ws_bytes if self.gp_persistent else 0)
+                 workspace=ws if self.gp_algo else None, workspace_bytes=ws_bytes if self.gp_algo else 0, algo=self.gp_algo)
         # K_xy and mu = K_xy @ alpha for every decoder item: query image i, support image (i + b) % E
         kxy = self.buf("gp.kxy", (D, n, ldw), dtype=torch.float32)
         dim = arch.DEC_DIM

@@ -18,7 +18,7 @@ ws = torch.empty(ws_floats, device=dev)
 def gp(persistent=True):
     W.copy_(W0)
     call("romab200_gp_solve", "rb_gp_solve_args", W=W, n=n, nrhs=nrhs, batch=batch, ldw=n, stride=(n + nrhs) * n,
-         workspace=ws if persistent else None, workspace_bytes=ws_floats * 4 if persistent else 0)
+         workspace=ws if persistent else None, workspace_bytes=ws_floats * 4 if persistent else 0, algo=1 if persistent else 0)
 
 M, N, K = 95048, 256, 2304
 A = torch.randn(M, K, device=dev).half(); B = torch.randn(N, K, device=dev).half(); C = torch.empty(M, N, device=dev, dtype=torch.float16)

@@ -105,7 +105,7 @@ def test_engine_dry_run(weights, monkeypatch, symmetric, upsample):
     eng.device = torch.device("cpu")
     eng.precision, eng.dtype, eng.dt = "fp32", torch.float32, cabi.RB_F32
     eng.w = PackedWeights(weights[0], weights[1], eng.device, torch.float32)
-    eng._buf, eng._const, eng.debug, eng.profile, eng.gemm_profile, eng.use_flash_attn, eng.gp_persistent = {}, {}, None, None, None, True, True
+    eng._buf, eng._const, eng.debug, eng.profile, eng.gemm_profile, eng.use_flash_attn, eng.gp_algo = {}, {}, None, None, None, True, 2
     eng.overlap_cnn, eng._side, eng.gp_tensor_core, eng.fused_c144 = False, None, True, True
     for t in _tensors(eng.w):
         rec.track(t)

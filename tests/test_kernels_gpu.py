@@ -194,9 +194,9 @@ def test_conv_first_and_maxpool():
 
 
 # ----------------------------------------------------------------------------------------------- GP solve
-@pytest.mark.parametrize("persistent", [False, True])
-@pytest.mark.parametrize("n,nrhs,batch", [(64, 40, 2), (100, 512, 1), (1600, 512, 2), (224, 70, 3)])
-def test_gp_solve(n, nrhs, batch, persistent):
+@pytest.mark.parametrize("algo", [0, 1, 2])
+@pytest.mark.parametrize("n,nrhs,batch", [(64, 40, 2), (100, 512, 1), (1600, 512, 2), (224, 70, 3), (1408, 512, 2)])
+def test_gp_solve(n, nrhs, batch, algo):
     g = torch.Generator().manual_seed(n)
     feats = torch.randn(batch, n, 48, generator=g)
     feats = feats / feats.norm(dim=-1, keepdim=True)
@@ -208,15 +208,15 @@ def test_gp_solve(n, nrhs, batch, persistent):
     Wk[:, :n, :n] = Kyy
     Wk[:, n:, :n] = Fm.t()
     Wk = Wk.to(DEV)
-    ws_floats = batch * ((n + 31) // 32) * 1024 + 1
+    ws_floats = max(batch * ((n + 31) // 32) * 1024 + 1, batch * ((n + 127) // 128) * 16384)
     ws = torch.empty(ws_floats, device=DEV)
     call("romab200_gp_solve", "rb_gp_solve_args", W=Wk, n=n, nrhs=nrhs, batch=batch, ldw=ldw, stride=(n + nrhs) * ldw,
-         workspace=ws if persistent else None, workspace_bytes=ws_floats * 4 if persistent else 0)
+         workspace=ws if algo else None, workspace_bytes=ws_floats * 4 if algo else 0, algo=algo)
     torch.cuda.synchronize()
     alpha_t = Wk[:, n:, :n].cpu()
     err = (alpha_t.transpose(1, 2).double() - ref).abs().max().item()
     assert err < 5e-4 * ref.abs().max().item(), err
-    if not persistent:       # in-place variant: the lower triangle now holds the Cholesky factor
+    if algo != 1:            # in-place variants: the lower triangle now holds the Cholesky factor
         L = torch.tril(Wk[:, :n, :n].cpu().double())
         close((L @ L.transpose(1, 2)).float(), Kyy, 1e-5)
 
