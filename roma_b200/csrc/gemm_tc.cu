@@ -174,6 +174,9 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the previous
+    // kernel in the stream; its results may only be touched after this point
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -439,7 +442,14 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, 
     p.total_tiles = (int)total;
     const int resident = sm_count() * Cfg::CTAS_PER_SM;
     const int grid = p.total_tiles < resident ? p.total_tiles : resident;
-    gemm_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(ma, mb, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, ma, mb, (const TcParams)p);
+    if (err != cudaSuccess) { set_error("gemm_tc: launch failed: %s", cudaGetErrorString(err)); return 1; }
     return check_launch("gemm_tc");
 }
 
