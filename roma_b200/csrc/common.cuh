@@ -1,5 +1,6 @@
 // Shared helpers for libromab200 kernels (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -111,6 +112,28 @@ struct Epilogue {
         store_any(C, orow * ldc + n, dtype_c, apply(acc, m, n, orow));
     }
 };
+
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the library is launched with the stream-serialization attribute and
+// starts with pdl_wait(), so that its launch latency and per-CTA set-up overlap the tail of the previous kernel in the
+// stream (the ~680 launches of one match() are otherwise separated by a few microseconds each).
+// ------------------------------------------------------------------------------------------------
+// No early griddepcontrol.launch_dependents: measured on B200 it costs 5 % of a match() (the next grid's CTAs take SM
+// slots and issue bandwidth while they spin in their wait); the implicit trigger at grid exit already hides the launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// ROMAB200_NO_PDL=1 launches every kernel fully serialised (debugging knob; griddepcontrol.* are no-ops then)
+inline int pdl_mode() { static const int m = [] { const char* e = getenv("ROMAB200_NO_PDL"); return e ? atoi(e) : 0; }(); return m; }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_mode() ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 int gemm_simt(const rb_gemm_args* a, cudaStream_t stream);
 int gemm_tc(const rb_gemm_args* a, cudaStream_t stream);

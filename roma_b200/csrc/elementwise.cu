@@ -11,6 +11,7 @@ namespace rb {
 template <typename TI, typename TO>
 __global__ void layernorm_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ g,
                                  const float* __restrict__ b, int64_t rows, int cols, int64_t ldx, int64_t ldy, float eps) {
+    rb::pdl_wait();
     int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     if (row >= rows) return;
     int lane = threadIdx.x & 31;
@@ -30,6 +31,7 @@ __global__ void layernorm_kernel(const TI* __restrict__ x, TO* __restrict__ y, c
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void softmax_rows_kernel(T* __restrict__ s, int64_t rows, int cols, int64_t lds, float scale) {
+    rb::pdl_wait();
     __shared__ float red[8];
     int64_t row = blockIdx.x;
     T* sr = s + row * lds;
@@ -59,6 +61,7 @@ __global__ void softmax_rows_kernel(T* __restrict__ s, int64_t rows, int cols, i
 // 16-byte loads, kept in registers, and written once.
 template <typename T>
 __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(T* __restrict__ s, int64_t rows, int cols, int64_t lds, float scale) {
+    rb::pdl_wait();
     constexpr int VN = 16 / sizeof(T);
     constexpr int ITERS = 2048 / (32 * VN);
     const int lane = threadIdx.x & 31;
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(T* __restrict__ 
 
 template <typename T>
 __global__ void row_norms_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t rows, int cols, int64_t ldx) {
+    rb::pdl_wait();
     int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     if (row >= rows) return;
     int lane = threadIdx.x & 31;
@@ -117,6 +121,7 @@ __global__ void row_norms_kernel(const T* __restrict__ x, float* __restrict__ ou
 
 __global__ void copy2d_kernel(const void* __restrict__ src, void* __restrict__ dst, int64_t rows, int cols, int64_t lds,
                               int64_t ldd, int ds, int dd, const float* __restrict__ row_scale, int recip) {
+    rb::pdl_wait();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = rows * cols;
     for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -130,6 +135,7 @@ __global__ void copy2d_kernel(const void* __restrict__ src, void* __restrict__ d
 // x / norm -> fp16 hi and lo parts laid out [hi|lo|hi] (A operand) or [hi|hi|lo] (B operand)
 __global__ void split_f16x3_kernel(const float* __restrict__ x, __half* __restrict__ dst, int64_t rows, int cols,
                                    int64_t ldx, int64_t ldd, const float* __restrict__ norm, int layout_b) {
+    rb::pdl_wait();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = rows * cols;
     for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -149,6 +155,7 @@ __global__ void split_f16x3_kernel(const float* __restrict__ x, __half* __restri
 // (same (c,ky,kx) order as Conv2d weight.flatten(1), patch_embed.py:69-82)
 template <typename TO>
 __global__ void im2col_patch_kernel(const float* __restrict__ img, TO* __restrict__ out, int B, int H, int W, int P, int64_t ldo) {
+    rb::pdl_wait();
     int hp = H / P, wp = W / P, kk = 3 * P * P;
     int64_t total = (int64_t)B * hp * wp * kk;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -163,6 +170,7 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, TO* __restric
 
 __global__ void assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
                                        const float* __restrict__ pos, float* __restrict__ tok, int B, int np, int dim) {
+    rb::pdl_wait();
     int64_t total = (int64_t)B * (np + 1) * dim;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -177,6 +185,7 @@ __global__ void assemble_tokens_kernel(const float* __restrict__ patch, const fl
 template <typename T>
 __global__ void transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, int rows, int cols, int64_t lds, int64_t ldd,
                                  int batch1, int64_t ss0, int64_t ss1, int64_t sd0, int64_t sd1) {
+    rb::pdl_wait();
     __shared__ T tile[32][33];
     int z = blockIdx.z, z0 = z / batch1, z1 = z % batch1;
     const T* s = src + z0 * ss0 + z1 * ss1;
@@ -207,7 +216,7 @@ extern "C" int romab200_layernorm(const rb_layernorm_args* a, void* stream) {
     RB_REQUIRE(a->rows > 0 && a->cols > 0, "layernorm: empty input");
     int wpb = 8;
     dim3 grid((unsigned)((a->rows + wpb - 1) / wpb));
-#define LN(TI, TO) layernorm_kernel<TI, TO><<<grid, wpb * 32, 0, st>>>((const TI*)a->x, (TO*)a->y, a->gamma, a->beta, a->rows, a->cols, a->ldx, a->ldy, a->eps)
+#define LN(TI, TO) rb::launch_pdl(layernorm_kernel<TI, TO>, dim3(grid), dim3(wpb * 32), 0, st, (const TI*)a->x, (TO*)a->y, a->gamma, a->beta, a->rows, a->cols, a->ldx, a->ldy, a->eps)
     if (a->dtype_x == RB_F32 && a->dtype_y == RB_F32) LN(float, float);
     else if (a->dtype_x == RB_F32 && a->dtype_y == RB_F16) LN(float, __half);
     else if (a->dtype_x == RB_F32 && a->dtype_y == RB_BF16) LN(float, __nv_bfloat16);
@@ -224,14 +233,14 @@ extern "C" int romab200_softmax_rows(const rb_softmax_args* a, void* stream) {
     // rows must be padded to whole 16-byte vectors (the pad columns are rewritten with zeros)
     if (a->cols <= 2048 && (a->lds * es) % 16 == 0 && ((uintptr_t)a->s) % 16 == 0 && (a->cols + vn - 1) / vn * vn <= a->lds) {
         unsigned grid = (unsigned)((a->rows + 7) / 8);
-        if (a->dtype == RB_F32) softmax_rows_warp_kernel<float><<<grid, 256, 0, st>>>((float*)a->s, a->rows, a->cols, a->lds, a->scale);
-        else if (a->dtype == RB_F16) softmax_rows_warp_kernel<__half><<<grid, 256, 0, st>>>((__half*)a->s, a->rows, a->cols, a->lds, a->scale);
-        else softmax_rows_warp_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)a->s, a->rows, a->cols, a->lds, a->scale);
+        if (a->dtype == RB_F32) rb::launch_pdl(softmax_rows_warp_kernel<float>, dim3(grid), dim3(256), 0, st, (float*)a->s, a->rows, a->cols, a->lds, a->scale);
+        else if (a->dtype == RB_F16) rb::launch_pdl(softmax_rows_warp_kernel<__half>, dim3(grid), dim3(256), 0, st, (__half*)a->s, a->rows, a->cols, a->lds, a->scale);
+        else rb::launch_pdl(softmax_rows_warp_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (__nv_bfloat16*)a->s, a->rows, a->cols, a->lds, a->scale);
         return check_launch("softmax_rows");
     }
-    if (a->dtype == RB_F32) softmax_rows_kernel<float><<<(unsigned)a->rows, 256, 0, st>>>((float*)a->s, a->rows, a->cols, a->lds, a->scale);
-    else if (a->dtype == RB_F16) softmax_rows_kernel<__half><<<(unsigned)a->rows, 256, 0, st>>>((__half*)a->s, a->rows, a->cols, a->lds, a->scale);
-    else softmax_rows_kernel<__nv_bfloat16><<<(unsigned)a->rows, 256, 0, st>>>((__nv_bfloat16*)a->s, a->rows, a->cols, a->lds, a->scale);
+    if (a->dtype == RB_F32) rb::launch_pdl(softmax_rows_kernel<float>, dim3((unsigned)a->rows), dim3(256), 0, st, (float*)a->s, a->rows, a->cols, a->lds, a->scale);
+    else if (a->dtype == RB_F16) rb::launch_pdl(softmax_rows_kernel<__half>, dim3((unsigned)a->rows), dim3(256), 0, st, (__half*)a->s, a->rows, a->cols, a->lds, a->scale);
+    else rb::launch_pdl(softmax_rows_kernel<__nv_bfloat16>, dim3((unsigned)a->rows), dim3(256), 0, st, (__nv_bfloat16*)a->s, a->rows, a->cols, a->lds, a->scale);
     return check_launch("softmax_rows");
 }
 
@@ -239,16 +248,16 @@ extern "C" int romab200_row_norms(const rb_rownorm_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->rows > 0 && a->cols > 0, "row_norms: empty input");
     dim3 grid((unsigned)((a->rows + 7) / 8));
-    if (a->dtype == RB_F32) row_norms_kernel<float><<<grid, 256, 0, st>>>((const float*)a->x, a->out, a->rows, a->cols, a->ldx);
-    else if (a->dtype == RB_F16) row_norms_kernel<__half><<<grid, 256, 0, st>>>((const __half*)a->x, a->out, a->rows, a->cols, a->ldx);
-    else row_norms_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->x, a->out, a->rows, a->cols, a->ldx);
+    if (a->dtype == RB_F32) rb::launch_pdl(row_norms_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)a->x, a->out, a->rows, a->cols, a->ldx);
+    else if (a->dtype == RB_F16) rb::launch_pdl(row_norms_kernel<__half>, dim3(grid), dim3(256), 0, st, (const __half*)a->x, a->out, a->rows, a->cols, a->ldx);
+    else rb::launch_pdl(row_norms_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)a->x, a->out, a->rows, a->cols, a->ldx);
     return check_launch("row_norms");
 }
 
 extern "C" int romab200_copy2d(const rb_copy2d_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->rows > 0 && a->cols > 0, "copy2d: empty input");
-    copy2d_kernel<<<grid_for(a->rows * a->cols, 256), 256, 0, st>>>(a->src, a->dst, a->rows, a->cols, a->lds, a->ldd,
+    rb::launch_pdl(copy2d_kernel, dim3(grid_for(a->rows * a->cols, 256)), dim3(256), 0, st, a->src, a->dst, a->rows, a->cols, a->lds, a->ldd,
                                                                    a->dtype_src, a->dtype_dst, a->row_scale, a->row_scale_reciprocal);
     return check_launch("copy2d");
 }
@@ -256,7 +265,7 @@ extern "C" int romab200_copy2d(const rb_copy2d_args* a, void* stream) {
 extern "C" int romab200_split_f16x3(const rb_split_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->rows > 0 && a->cols > 0 && a->ldd >= 3 * a->cols, "split_f16x3: bad shape");
-    split_f16x3_kernel<<<grid_for(a->rows * a->cols, 256), 256, 0, st>>>(a->x, (__half*)a->dst, a->rows, a->cols, a->ldx, a->ldd,
+    rb::launch_pdl(split_f16x3_kernel, dim3(grid_for(a->rows * a->cols, 256)), dim3(256), 0, st, a->x, (__half*)a->dst, a->rows, a->cols, a->ldx, a->ldd,
                                                                         a->row_norm, a->layout_b);
     return check_launch("split_f16x3");
 }
@@ -266,16 +275,16 @@ extern "C" int romab200_im2col_patch(const rb_im2col_args* a, void* stream) {
     RB_REQUIRE(a->height % a->patch == 0 && a->width % a->patch == 0, "im2col: %dx%d not a multiple of patch %d", a->height, a->width, a->patch);
     int64_t total = (int64_t)a->batch * (a->height / a->patch) * (a->width / a->patch) * 3 * a->patch * a->patch;
     int g = grid_for(total, 256);
-    if (a->dtype_out == RB_F32) im2col_patch_kernel<float><<<g, 256, 0, st>>>(a->image, (float*)a->out, a->batch, a->height, a->width, a->patch, a->ldo);
-    else if (a->dtype_out == RB_F16) im2col_patch_kernel<__half><<<g, 256, 0, st>>>(a->image, (__half*)a->out, a->batch, a->height, a->width, a->patch, a->ldo);
-    else im2col_patch_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(a->image, (__nv_bfloat16*)a->out, a->batch, a->height, a->width, a->patch, a->ldo);
+    if (a->dtype_out == RB_F32) rb::launch_pdl(im2col_patch_kernel<float>, dim3(g), dim3(256), 0, st, a->image, (float*)a->out, a->batch, a->height, a->width, a->patch, a->ldo);
+    else if (a->dtype_out == RB_F16) rb::launch_pdl(im2col_patch_kernel<__half>, dim3(g), dim3(256), 0, st, a->image, (__half*)a->out, a->batch, a->height, a->width, a->patch, a->ldo);
+    else rb::launch_pdl(im2col_patch_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, st, a->image, (__nv_bfloat16*)a->out, a->batch, a->height, a->width, a->patch, a->ldo);
     return check_launch("im2col_patch");
 }
 
 extern "C" int romab200_assemble_tokens(const rb_tokens_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int64_t total = (int64_t)a->batch * (a->npatch + 1) * a->dim;
-    assemble_tokens_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->patch, a->cls, a->pos, a->tokens, a->batch, a->npatch, a->dim);
+    rb::launch_pdl(assemble_tokens_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, a->patch, a->cls, a->pos, a->tokens, a->batch, a->npatch, a->dim);
     return check_launch("assemble_tokens");
 }
 
@@ -285,8 +294,8 @@ extern "C" int romab200_transpose(const rb_transpose_args* a, void* stream) {
     dim3 grid((a->cols + 31) / 32, (a->rows + 31) / 32, b0 * b1), block(32, 8);
     RB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "transpose: grid too large");
     if (a->dtype == RB_F32)
-        transpose_kernel<float><<<grid, block, 0, st>>>((const float*)a->src, (float*)a->dst, a->rows, a->cols, a->lds, a->ldd, b1, a->ss0, a->ss1, a->sd0, a->sd1);
+        rb::launch_pdl(transpose_kernel<float>, dim3(grid), dim3(block), 0, st, (const float*)a->src, (float*)a->dst, a->rows, a->cols, a->lds, a->ldd, b1, a->ss0, a->ss1, a->sd0, a->sd1);
     else
-        transpose_kernel<uint16_t><<<grid, block, 0, st>>>((const uint16_t*)a->src, (uint16_t*)a->dst, a->rows, a->cols, a->lds, a->ldd, b1, a->ss0, a->ss1, a->sd0, a->sd1);
+        rb::launch_pdl(transpose_kernel<uint16_t>, dim3(grid), dim3(block), 0, st, (const uint16_t*)a->src, (uint16_t*)a->dst, a->rows, a->cols, a->lds, a->ldd, b1, a->ss0, a->ss1, a->sd0, a->sd1);
     return check_launch("transpose");
 }

@@ -134,6 +134,7 @@ template <int D> struct FaCfg {
 
 template <int D, typename T>
 __global__ void __launch_bounds__(192, 1) flash_attn_kernel(const __grid_constant__ CUtensorMap map_qkv, const FaParams p) {
+    rb::pdl_wait();
     using namespace fa;
     using Cfg = FaCfg<D>;
     constexpr int STAGES = Cfg::STAGES, BQ = Cfg::BQ, BKV = Cfg::BKV, DB = D / 64;
@@ -330,7 +331,7 @@ static int launch_fa(const CUtensorMap& map, const FaParams& p, int batch, cudaS
         configured = true;
     }
     dim3 grid((p.N + Cfg::BQ - 1) / Cfg::BQ, p.heads, batch);
-    flash_attn_kernel<D, T><<<grid, 192, Cfg::SMEM, st>>>(map, p);
+    rb::launch_pdl(flash_attn_kernel<D, T>, dim3(grid), dim3(192), Cfg::SMEM, st, map, p);
     return check_launch("flash_attn");
 }
 

@@ -41,6 +41,7 @@ constexpr int BK = 16;
 
 template <int BM, int BN, int TN>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
+    rb::pdl_wait();
     constexpr int TM = 8;
     constexpr int NT_N = BN / TN;            // threads along n
     constexpr int LDA_S = BM + 4;
@@ -249,13 +250,13 @@ int gemm_simt(const rb_gemm_args* a, cudaStream_t stream) {
     RB_REQUIRE(zdim <= 65535, "gemm_simt: batch %d too large", zdim);
     if (a->N <= 32) {
         dim3 grid((a->M + 255) / 256, (a->N + 31) / 32, zdim);
-        gemm_simt_kernel<256, 32, 4><<<grid, 256, 0, stream>>>(p);
+        rb::launch_pdl(gemm_simt_kernel<256, 32, 4>, dim3(grid), dim3(256), 0, stream, p);
     } else if (a->N <= 64) {
         dim3 grid((a->M + 127) / 128, (a->N + 63) / 64, zdim);
-        gemm_simt_kernel<128, 64, 4><<<grid, 256, 0, stream>>>(p);
+        rb::launch_pdl(gemm_simt_kernel<128, 64, 4>, dim3(grid), dim3(256), 0, stream, p);
     } else {
         dim3 grid((a->M + 127) / 128, (a->N + 127) / 128, zdim);
-        gemm_simt_kernel<128, 128, 8><<<grid, 256, 0, stream>>>(p);
+        rb::launch_pdl(gemm_simt_kernel<128, 128, 8>, dim3(grid), dim3(256), 0, stream, p);
     }
     return check_launch("gemm_simt");
 }

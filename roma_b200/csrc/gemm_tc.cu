@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __
     const uint32_t tmem_base = *tmem_slot;
     // programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the previous
     // kernel in the stream; its results may only be touched after this point
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    rb::pdl_wait();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -447,7 +447,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, 
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = rb::pdl_mode() == 1 ? 0 : 1;
     cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, ma, mb, (const TcParams)p);
     if (err != cudaSuccess) { set_error("gemm_tc: launch failed: %s", cudaGetErrorString(err)); return 1; }
     return check_launch("gemm_tc");

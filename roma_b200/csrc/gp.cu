@@ -49,6 +49,7 @@ __device__ void factor_diag_block(const float* __restrict__ Wd, int64_t ldw, int
 
 // one warp per problem: factor the diagonal block in place
 __global__ void __launch_bounds__(32) chol_diag_kernel(float* __restrict__ W, int64_t ldw, int64_t stride, int k, int bs) {
+    rb::pdl_wait();
     __shared__ float L[NB][NB + 1];
     float* Wd = W + (int64_t)blockIdx.x * stride + (int64_t)k * ldw + k;
     factor_diag_block(Wd, ldw, bs, L, Wd);
@@ -67,6 +68,7 @@ __device__ __forceinline__ void load_diag_block(const float* __restrict__ Wd, in
 // grid: (row_blocks, batch); block 128 threads: one thread per row below the (already factored) diagonal
 // block solves x * L^T = a with the 32-step recurrence held in registers.
 __global__ void __launch_bounds__(128) chol_panel_kernel(float* __restrict__ W, int64_t ldw, int64_t stride, int k, int bs, int total_rows) {
+    rb::pdl_wait();
     __shared__ float L[NB][NB + 1];
     float* Wb = W + (int64_t)blockIdx.y * stride;
     load_diag_block(Wb + (int64_t)k * ldw + k, ldw, bs, L);
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(float* __restrict__ W, 
 
 // backward substitution panel: rows of the RHS block solve x * L_kk = y (L_kk lower, bs x bs)
 __global__ void __launch_bounds__(128) trsm_back_kernel(float* __restrict__ W, int64_t ldw, int64_t stride, int k, int bs, int n, int nrhs) {
+    rb::pdl_wait();
     __shared__ float L[NB][NB + 1];
     float* Wb = W + (int64_t)blockIdx.y * stride;
     load_diag_block(Wb + (int64_t)k * ldw + k, ldw, bs, L);
@@ -370,6 +373,7 @@ __device__ __forceinline__ void mm32_acc(const float* __restrict__ A, int lda, c
 
 __global__ void __launch_bounds__(256) chol_block128_kernel(float* __restrict__ W, float* __restrict__ inv_ws, int64_t ldw, int64_t stride,
                                                             int64_t ws_stride, int k, int kb, int bs) {
+    rb::pdl_wait();
     extern __shared__ float sm128[];
     float (*S)[BBP] = reinterpret_cast<float (*)[BBP]>(sm128);                    // the block, then its factor L
     float (*V)[BBP] = reinterpret_cast<float (*)[BBP]>(sm128 + BB * BBP);         // L^-1
@@ -501,7 +505,7 @@ static int gp_solve_block128(const rb_gp_solve_args* a, cudaStream_t st) {
     }
     for (int kb = 0; kb < nblk; ++kb) {
         const int k = kb * BB, bs = n - k < BB ? n - k : BB;
-        chol_block128_kernel<<<a->batch, 256, smem, st>>>(W, ws, a->ldw, a->stride, ws_stride, k, kb, bs);
+        rb::launch_pdl(chol_block128_kernel, dim3(a->batch), dim3(256), smem, st, W, ws, a->ldw, a->stride, ws_stride, k, kb, bs);
         if (check_launch("chol_block128")) return 1;
         const int below = total - (k + bs);
         if (below > 0) {
@@ -568,10 +572,10 @@ extern "C" int romab200_gp_solve(const rb_gp_solve_args* a, void* stream) {
     for (int k = 0; k < n; k += NB) {
         int bs = n - k < NB ? n - k : NB;
         int below = total - (k + bs);
-        chol_diag_kernel<<<a->batch, 32, 0, st>>>(W, a->ldw, a->stride, k, bs);
+        rb::launch_pdl(chol_diag_kernel, dim3(a->batch), dim3(32), 0, st, W, a->ldw, a->stride, k, bs);
         if (check_launch("chol_diag")) return 1;
         dim3 grid((below + 127) / 128, a->batch);
-        chol_panel_kernel<<<grid, 128, 0, st>>>(W, a->ldw, a->stride, k, bs, total);
+        rb::launch_pdl(chol_panel_kernel, dim3(grid), dim3(128), 0, st, W, a->ldw, a->stride, k, bs, total);
         if (check_launch("chol_panel")) return 1;
         int nt = n - (k + bs);
         if (nt > 0) {
@@ -585,7 +589,7 @@ extern "C" int romab200_gp_solve(const rb_gp_solve_args* a, void* stream) {
     for (int k = last; k >= 0; k -= NB) {
         int bs = n - k < NB ? n - k : NB;
         dim3 grid((a->nrhs + 127) / 128, a->batch);
-        trsm_back_kernel<<<grid, 128, 0, st>>>(W, a->ldw, a->stride, k, bs, n, a->nrhs);
+        rb::launch_pdl(trsm_back_kernel, dim3(grid), dim3(128), 0, st, W, a->ldw, a->stride, k, bs, n, a->nrhs);
         if (check_launch("trsm_back")) return 1;
         if (k > 0) {
             float* X = W + (int64_t)n * a->ldw + k;                  // solved block  [nrhs, bs]

@@ -12,6 +12,7 @@ __device__ __forceinline__ float rh(float v) { return __half2float(__float2half_
 //   d2 = fp16( fp32-accumulated  [-2x | ||x||^2 | 1] . [y | 1 | ||y||^2] ),  d = fp16(sqrt(max(d2, 0)))
 // then fp16(d*d), fp16(-. / (2 std^2)), fp16(exp(.)), fp32 row sum rounded to fp16.
 __global__ void __launch_bounds__(128) kde_kernel(const float* __restrict__ x, float* __restrict__ density, int n, float two_var, int half) {
+    rb::pdl_wait();
     __shared__ float4 pts[512];
     __shared__ float nrm[512];
     const int i = blockIdx.x * 128 + threadIdx.x;
@@ -82,6 +83,6 @@ extern "C" int romab200_kde_density(const rb_kde_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->n > 0 && ((uintptr_t)a->x) % 16 == 0, "kde_density: n=%d or unaligned input", a->n);
     float two_var = (float)(2.0 * (double)a->std * (double)a->std);
-    kde_kernel<<<(a->n + 127) / 128, 128, 0, st>>>(a->x, a->density, a->n, two_var, a->half);
+    rb::launch_pdl(kde_kernel, dim3((a->n + 127) / 128), dim3(128), 0, st, a->x, a->density, a->n, two_var, a->half);
     return check_launch("kde_density");
 }

@@ -128,6 +128,7 @@ struct PrologueParams {
 // registers and written with 16-byte stores (a warp per pixel would leave 3/4 of the lanes idle on 1.5 M pixels)
 template <typename T>
 __global__ void __launch_bounds__(256) refiner_prologue_small_kernel(const PrologueParams p) {
+    rb::pdl_wait();
     constexpr int MAXC = 32;
     const int64_t pix = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t hw = (int64_t)p.h * p.w;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(256) refiner_prologue_small_kernel(const Prolo
 
 template <typename T, int R>
 __global__ void __launch_bounds__(128) refiner_prologue_kernel(const PrologueParams p) {
+    rb::pdl_wait();
     constexpr int S = 2 * R + 2;
     __shared__ float dtab_all[4][R > 0 ? S * S : 1];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -263,6 +265,7 @@ struct LocalCorrParams {
 };
 template <typename T, int R, typename TO>
 __global__ void __launch_bounds__(128) local_corr_kernel(const LocalCorrParams p) {
+    rb::pdl_wait();
     constexpr int S = 2 * R + 2;
     __shared__ float dtab_all[4][S * S];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -287,6 +290,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) dwconv5x5_relu_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t ldi, int64_t ldo,
                                                              const float* __restrict__ wgt, int64_t ldw, const float* __restrict__ bias,
                                                              int H, int W, int C, int tiles_x) {
+    rb::pdl_wait();
     constexpr int TH = 8, TW = 16, CH = 32;
     __shared__ float tile[TH + 4][TW + 4][CH];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -338,6 +342,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) dwconv5x5_relu_h2_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t ldi, int64_t ldo,
                                                                 const float* __restrict__ wgt, int64_t ldw, const float* __restrict__ bias,
                                                                 int H, int W, int C, int tiles_x) {
+    rb::pdl_wait();
     // 4 warps, each owns TWO adjacent output rows of the 8x16 tile: the 6 input rows they need are read once
     // (120 LDS.32 per 64 outputs instead of 200), so the FP32 FMA pipe is the limiter.
     constexpr int TH = 8, TW = 16, CH = 64, NT = 128;
@@ -428,6 +433,7 @@ __global__ void __launch_bounds__(256) refiner_block_small_kernel(const T* __res
                                                                   const float* __restrict__ dw_w, int64_t ldw, const float* __restrict__ dw_b,
                                                                   const float* __restrict__ pw_w, const float* __restrict__ pw_b,
                                                                   int H, int W, int tiles_x) {
+    rb::pdl_wait();
     constexpr int TS = 16, IN = TS + 4, CP = C / 2;
     constexpr int PS = C + 2;                 // input pixel stride in halves (odd number of 32-bit words: conflict-free)
     constexpr int MS = C + 1;                 // mid pixel stride in floats
@@ -538,6 +544,7 @@ template <typename T, int LPP>
 __global__ void __launch_bounds__(256) refiner_tail_kernel(const T* __restrict__ d, int64_t ldd, const float* __restrict__ wgt, int64_t ldw,
                                                            const float* __restrict__ bias, float* __restrict__ state, int64_t rows, int C,
                                                            float sx, float sy, float* __restrict__ delta_out) {
+    rb::pdl_wait();
     constexpr int VN = Vec16<T>::N;
     const int sub = threadIdx.x % LPP;
     const int64_t row = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPP;
@@ -589,6 +596,7 @@ __device__ __forceinline__ void bilinear_src(int dst, int in_size, int out_size,
 }
 
 __global__ void bilinear_resize_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int hi, int wi, int ho, int wo, int C) {
+    rb::pdl_wait();
     int64_t total = (int64_t)B * ho * wo * C;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -610,6 +618,7 @@ __global__ void bilinear_resize_kernel(const float* __restrict__ in, float* __re
 // --------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) cls_to_flow_kernel(const T* __restrict__ logits, float* __restrict__ state, int64_t ldl, int res) {
+    rb::pdl_wait();
     __shared__ float smax[8]; __shared__ int sidx[8]; __shared__ float ssum[8];
     const int C = res * res;
     const int64_t row = blockIdx.x;
@@ -659,6 +668,7 @@ __global__ void __launch_bounds__(256) cls_to_flow_kernel(const T* __restrict__ 
 __global__ void match_epilogue_kernel(const float* __restrict__ state, const float* __restrict__ coarse, int hc, int wc,
                                       float* __restrict__ warp, float* __restrict__ cert, int b, int H, int W, int symmetric,
                                       const float* __restrict__ gx, const float* __restrict__ gy) {
+    rb::pdl_wait();
     const int D = symmetric ? 2 * b : b;
     int64_t total = (int64_t)D * H * W;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -718,12 +728,12 @@ extern "C" int romab200_refiner_prologue(const rb_refiner_prologue_args* a, void
     int64_t pixels = (int64_t)a->D * a->h * a->w;
     if (a->radius == 0 && 2 * a->cf + a->emb <= 32 && a->ldd <= 32 && p.vec_ok && a->dtype != RB_F32) {
         unsigned g = (unsigned)((pixels + 255) / 256);
-        if (a->dtype == RB_F16) refiner_prologue_small_kernel<__half><<<g, 256, 0, st>>>(p);
-        else refiner_prologue_small_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(p);
+        if (a->dtype == RB_F16) rb::launch_pdl(refiner_prologue_small_kernel<__half>, dim3(g), dim3(256), 0, st, p);
+        else rb::launch_pdl(refiner_prologue_small_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, st, p);
         return check_launch("refiner_prologue_small");
     }
     unsigned grid = (unsigned)((pixels + 3) / 4);
-#define LAUNCH(T, R) refiner_prologue_kernel<T, R><<<grid, 128, 0, st>>>(p)
+#define LAUNCH(T, R) rb::launch_pdl(refiner_prologue_kernel<T, R>, dim3(grid), dim3(128), 0, st, p)
 #define BYR(T)                                                                                        \
     switch (a->radius) {                                                                              \
         case 0: LAUNCH(T, 0); break; case 2: LAUNCH(T, 2); break; case 3: LAUNCH(T, 3); break;        \
@@ -748,7 +758,7 @@ extern "C" int romab200_local_corr(const rb_local_corr_args* a, void* stream) {
     p.scale = a->scale; p.n_img = a->n_img > 0 ? a->n_img : a->batch; p.y_shift = a->y_shift; p.winx = a->win_x; p.winy = a->win_y;
     int64_t pixels = (int64_t)a->batch * a->h * a->w;
     unsigned grid = (unsigned)((pixels + 3) / 4);
-#define LAUNCH(T, R, TO) local_corr_kernel<T, R, TO><<<grid, 128, 0, st>>>(p)
+#define LAUNCH(T, R, TO) rb::launch_pdl(local_corr_kernel<T, R, TO>, dim3(grid), dim3(128), 0, st, p)
 #define BYR(T, TO)                                                                                    \
     switch (a->radius) {                                                                              \
         case 2: LAUNCH(T, 2, TO); break; case 3: LAUNCH(T, 3, TO); break; case 7: LAUNCH(T, 7, TO); break; \
@@ -771,13 +781,13 @@ extern "C" int romab200_dwconv5x5_relu(const rb_dwconv_args* a, void* stream) {
     if (a->dtype != RB_F32 && a->ldi % 8 == 0 && a->ldo % 2 == 0 && a->ldi >= cpad && a->ldo >= cpad &&
         ((uintptr_t)a->in) % 16 == 0 && ((uintptr_t)a->out) % 4 == 0) {
         dim3 grid2(tiles_x * tiles_y, (a->c + 63) / 64, a->batch);
-        if (a->dtype == RB_F16) dwconv5x5_relu_h2_kernel<__half><<<grid2, 128, 0, st>>>((const __half*)a->in, (__half*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
-        else dwconv5x5_relu_h2_kernel<__nv_bfloat16><<<grid2, 128, 0, st>>>((const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
+        if (a->dtype == RB_F16) rb::launch_pdl(dwconv5x5_relu_h2_kernel<__half>, dim3(grid2), dim3(128), 0, st, (const __half*)a->in, (__half*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
+        else rb::launch_pdl(dwconv5x5_relu_h2_kernel<__nv_bfloat16>, dim3(grid2), dim3(128), 0, st, (const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
         return check_launch("dwconv5x5_relu");
     }
-    if (a->dtype == RB_F32) dwconv5x5_relu_kernel<float><<<grid, 256, 0, st>>>((const float*)a->in, (float*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
-    else if (a->dtype == RB_F16) dwconv5x5_relu_kernel<__half><<<grid, 256, 0, st>>>((const __half*)a->in, (__half*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
-    else dwconv5x5_relu_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
+    if (a->dtype == RB_F32) rb::launch_pdl(dwconv5x5_relu_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)a->in, (float*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
+    else if (a->dtype == RB_F16) rb::launch_pdl(dwconv5x5_relu_kernel<__half>, dim3(grid), dim3(256), 0, st, (const __half*)a->in, (__half*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
+    else rb::launch_pdl(dwconv5x5_relu_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
     return check_launch("dwconv5x5_relu");
 }
 
@@ -790,10 +800,10 @@ extern "C" int romab200_refiner_block_small(const rb_refiner_block_small_args* a
     dim3 grid(tiles_x * tiles_y, a->batch);
     RB_REQUIRE(grid.y <= 65535, "refiner_block_small: batch too large");
     if (a->dtype == RB_F16)
-        refiner_block_small_kernel<__half, 24><<<grid, 256, 0, st>>>((const __half*)a->in, (__half*)a->out, a->ld, a->dw_weight, a->ldw, a->dw_bias,
+        rb::launch_pdl(refiner_block_small_kernel<__half, 24>, dim3(grid), dim3(256), 0, st, (const __half*)a->in, (__half*)a->out, a->ld, a->dw_weight, a->ldw, a->dw_bias,
                                                                      a->pw_weight, a->pw_bias, a->h, a->w, tiles_x);
     else
-        refiner_block_small_kernel<__nv_bfloat16, 24><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ld, a->dw_weight,
+        rb::launch_pdl(refiner_block_small_kernel<__nv_bfloat16, 24>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ld, a->dw_weight,
                                                                             a->ldw, a->dw_bias, a->pw_weight, a->pw_bias, a->h, a->w, tiles_x);
     return check_launch("refiner_block_small");
 }
@@ -807,7 +817,7 @@ extern "C" int romab200_refiner_tail(const rb_refiner_tail_args* a, void* stream
                a->c, (long long)a->ldd, (long long)a->ldw);
     const int lpp = a->c <= 32 ? 4 : (a->c <= 256 ? 8 : 32);
     unsigned grid = (unsigned)((a->rows * lpp + 255) / 256);
-#define TAIL(T, L) refiner_tail_kernel<T, L><<<grid, 256, 0, st>>>((const T*)a->d, a->ldd, a->weight, a->ldw, a->bias, a->state, a->rows, a->c, a->scale_x, a->scale_y, a->delta_out)
+#define TAIL(T, L) rb::launch_pdl(refiner_tail_kernel<T, L>, dim3(grid), dim3(256), 0, st, (const T*)a->d, a->ldd, a->weight, a->ldw, a->bias, a->state, a->rows, a->c, a->scale_x, a->scale_y, a->delta_out)
 #define BYL(T) if (lpp == 4) TAIL(T, 4); else if (lpp == 8) TAIL(T, 8); else TAIL(T, 32);
     if (a->dtype == RB_F32) { BYL(float) } else if (a->dtype == RB_F16) { BYL(__half) } else { BYL(__nv_bfloat16) }
 #undef BYL
@@ -819,16 +829,16 @@ extern "C" int romab200_bilinear_resize(const rb_resize_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int64_t total = (int64_t)a->batch * a->ho * a->wo * a->c;
     RB_REQUIRE(total > 0, "bilinear_resize: empty");
-    bilinear_resize_kernel<<<grid1d(total, 256), 256, 0, st>>>(a->in, a->out, a->batch, a->hi, a->wi, a->ho, a->wo, a->c);
+    rb::launch_pdl(bilinear_resize_kernel, dim3(grid1d(total, 256)), dim3(256), 0, st, a->in, a->out, a->batch, a->hi, a->wi, a->ho, a->wo, a->c);
     return check_launch("bilinear_resize");
 }
 
 extern "C" int romab200_cls_to_flow_refine(const rb_cls_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->rows > 0 && a->rows < (1ll << 31) && a->ldl > (int64_t)a->res * a->res, "cls_to_flow_refine: bad shape");
-    if (a->dtype == RB_F32) cls_to_flow_kernel<float><<<(unsigned)a->rows, 256, 0, st>>>((const float*)a->logits, a->state, a->ldl, a->res);
-    else if (a->dtype == RB_F16) cls_to_flow_kernel<__half><<<(unsigned)a->rows, 256, 0, st>>>((const __half*)a->logits, a->state, a->ldl, a->res);
-    else cls_to_flow_kernel<__nv_bfloat16><<<(unsigned)a->rows, 256, 0, st>>>((const __nv_bfloat16*)a->logits, a->state, a->ldl, a->res);
+    if (a->dtype == RB_F32) rb::launch_pdl(cls_to_flow_kernel<float>, dim3((unsigned)a->rows), dim3(256), 0, st, (const float*)a->logits, a->state, a->ldl, a->res);
+    else if (a->dtype == RB_F16) rb::launch_pdl(cls_to_flow_kernel<__half>, dim3((unsigned)a->rows), dim3(256), 0, st, (const __half*)a->logits, a->state, a->ldl, a->res);
+    else rb::launch_pdl(cls_to_flow_kernel<__nv_bfloat16>, dim3((unsigned)a->rows), dim3(256), 0, st, (const __nv_bfloat16*)a->logits, a->state, a->ldl, a->res);
     return check_launch("cls_to_flow_refine");
 }
 
@@ -837,7 +847,7 @@ extern "C" int romab200_match_epilogue(const rb_match_epilogue_args* a, void* st
     int D = a->symmetric ? 2 * a->b : a->b;
     int64_t total = (int64_t)D * a->H * a->W;
     RB_REQUIRE(total > 0 && a->grid_x && a->grid_y, "match_epilogue: bad arguments");
-    match_epilogue_kernel<<<grid1d(total, 256), 256, 0, st>>>(a->state, a->coarse_state, a->hc, a->wc, a->warp, a->cert, a->b, a->H, a->W,
+    rb::launch_pdl(match_epilogue_kernel, dim3(grid1d(total, 256)), dim3(256), 0, st, a->state, a->coarse_state, a->hc, a->wc, a->warp, a->cert, a->b, a->H, a->W,
                                                               a->symmetric, a->grid_x, a->grid_y);
     return check_launch("match_epilogue");
 }

@@ -106,6 +106,7 @@ constexpr int FZ_SMEM = FZ_A_BYTES + FZ_B_BYTES + FZ_IN_BYTES + FZ_W_BYTES + 102
 
 template <typename T>
 __global__ void __launch_bounds__(FZ_THREADS, 1) refiner_block_c144_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParams p) {
+    rb::pdl_wait();
     using namespace fz;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -328,11 +329,11 @@ extern "C" int romab200_refiner_block_c144(const rb_refiner_block_c144_args* a, 
     if (a->dtype == RB_F16) {
         static bool cfg = false;
         if (!cfg) { RB_REQUIRE(cudaFuncSetAttribute(refiner_block_c144_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM) == cudaSuccess, "refiner_block_c144: smem attribute"); cfg = true; }
-        refiner_block_c144_kernel<__half><<<grid, FZ_THREADS, FZ_SMEM, st>>>(map, p);
+        rb::launch_pdl(refiner_block_c144_kernel<__half>, dim3(grid), dim3(FZ_THREADS), FZ_SMEM, st, map, p);
     } else {
         static bool cfg = false;
         if (!cfg) { RB_REQUIRE(cudaFuncSetAttribute(refiner_block_c144_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM) == cudaSuccess, "refiner_block_c144: smem attribute"); cfg = true; }
-        refiner_block_c144_kernel<__nv_bfloat16><<<grid, FZ_THREADS, FZ_SMEM, st>>>(map, p);
+        rb::launch_pdl(refiner_block_c144_kernel<__nv_bfloat16>, dim3(grid), dim3(FZ_THREADS), FZ_SMEM, st, map, p);
     }
     return check_launch("refiner_block_c144");
 }

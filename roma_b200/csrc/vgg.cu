@@ -13,6 +13,7 @@ template <typename TO>
 __global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restrict__ img, TO* __restrict__ out,
                                                             const float* __restrict__ wgt, const float* __restrict__ bias,
                                                             int B, int H, int W, int COUT) {
+    rb::pdl_wait();
     extern __shared__ float sw[];   // [COUT][27] + [COUT]
     for (int i = threadIdx.x; i < COUT * 27; i += blockDim.x) sw[i] = wgt[i];
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) sw[COUT * 27 + i] = bias[i];
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restr
 // thread per (output pixel, channel); channels fastest -> coalesced
 template <typename T>
 __global__ void maxpool2x2_padded_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C) {
+    rb::pdl_wait();
     int Ho = H / 2, Wo = W / 2;
     int64_t total = (int64_t)B * Ho * Wo * C;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,9 +83,9 @@ extern "C" int romab200_conv3x3_first(const rb_conv_first_args* a, void* stream)
     RB_REQUIRE(a->height <= 65535 && a->batch <= 65535, "conv3x3_first: grid too large");
     dim3 grid((a->width + 127) / 128, a->height, a->batch);
     size_t smem = (size_t)a->cout * 28 * sizeof(float);
-    if (a->dtype_out == RB_F32) conv3x3_first_kernel<float><<<grid, 128, smem, st>>>(a->image, (float*)a->out, a->weight, a->bias, a->batch, a->height, a->width, a->cout);
-    else if (a->dtype_out == RB_F16) conv3x3_first_kernel<__half><<<grid, 128, smem, st>>>(a->image, (__half*)a->out, a->weight, a->bias, a->batch, a->height, a->width, a->cout);
-    else conv3x3_first_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>(a->image, (__nv_bfloat16*)a->out, a->weight, a->bias, a->batch, a->height, a->width, a->cout);
+    if (a->dtype_out == RB_F32) rb::launch_pdl(conv3x3_first_kernel<float>, dim3(grid), dim3(128), smem, st, a->image, (float*)a->out, a->weight, a->bias, a->batch, a->height, a->width, a->cout);
+    else if (a->dtype_out == RB_F16) rb::launch_pdl(conv3x3_first_kernel<__half>, dim3(grid), dim3(128), smem, st, a->image, (__half*)a->out, a->weight, a->bias, a->batch, a->height, a->width, a->cout);
+    else rb::launch_pdl(conv3x3_first_kernel<__nv_bfloat16>, dim3(grid), dim3(128), smem, st, a->image, (__nv_bfloat16*)a->out, a->weight, a->bias, a->batch, a->height, a->width, a->cout);
     return check_launch("conv3x3_first");
 }
 
@@ -92,8 +94,8 @@ extern "C" int romab200_maxpool2x2_padded(const rb_maxpool_args* a, void* stream
     int64_t total = (int64_t)a->batch * (a->height / 2) * (a->width / 2) * a->channels;
     RB_REQUIRE(total > 0, "maxpool: empty");
     int64_t g = (total + 255) / 256; if (g > 148 * 64) g = 148 * 64;
-    if (a->dtype == RB_F32) maxpool2x2_padded_kernel<float><<<(unsigned)g, 256, 0, st>>>((const float*)a->in, (float*)a->out, a->batch, a->height, a->width, a->channels);
-    else if (a->dtype == RB_F16) maxpool2x2_padded_kernel<__half><<<(unsigned)g, 256, 0, st>>>((const __half*)a->in, (__half*)a->out, a->batch, a->height, a->width, a->channels);
-    else maxpool2x2_padded_kernel<__nv_bfloat16><<<(unsigned)g, 256, 0, st>>>((const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->batch, a->height, a->width, a->channels);
+    if (a->dtype == RB_F32) rb::launch_pdl(maxpool2x2_padded_kernel<float>, dim3((unsigned)g), dim3(256), 0, st, (const float*)a->in, (float*)a->out, a->batch, a->height, a->width, a->channels);
+    else if (a->dtype == RB_F16) rb::launch_pdl(maxpool2x2_padded_kernel<__half>, dim3((unsigned)g), dim3(256), 0, st, (const __half*)a->in, (__half*)a->out, a->batch, a->height, a->width, a->channels);
+    else rb::launch_pdl(maxpool2x2_padded_kernel<__nv_bfloat16>, dim3((unsigned)g), dim3(256), 0, st, (const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->batch, a->height, a->width, a->channels);
     return check_launch("maxpool2x2_padded");
 }

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gemm_tc_gpu.py -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/tc.log 2>&1; echo "tc rc=$?"; tail -n 5 gpurun_out/tc.log
-timeout 300 python scripts/gemm_bench.py all > gpurun_out/gemm_bench.log 2>&1; cat gpurun_out/gemm_bench.log
-timeout 600 python -m pytest tests/test_e2e_gpu.py -m gpu -q -s --tb=short -p no:cacheprovider > gpurun_out/e2e.log 2>&1; grep -E "^\[|passed|failed|Error" gpurun_out/e2e.log | tail -n 12
-timeout 600 python bench.py --precision fp16 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_fp16.json 2> gpurun_out/bench_fp16.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_fp16.json')); print(d['value'], d['ms_per_step'], d['e2e']['value']); print(d['stage_ms_per_step']); print(d['roofline']['achieved'], d['roofline']['frac'])"; tail -n 3 gpurun_out/bench_fp16.err
+for i in 1 2 3; do timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_gemm_tc_gpu.py -m gpu -q -p no:cacheprovider 2>&1 | grep -E "AssertionError: max|passed|failed|^FAILED" | tr '\n' ' '; echo; done
+timeout 900 python -m pytest tests/test_e2e_gpu.py -m gpu -q -s --tb=short -p no:cacheprovider > gpurun_out/e2e.log 2>&1; grep -E "^\[|passed|failed|Error" gpurun_out/e2e.log | tail -n 14
+timeout 600 python bench.py --precision fp16 --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_fp16.json 2> gpurun_out/bench_fp16.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_fp16.json')); print(d['value'], d['ms_per_step'], d['e2e']['value']); print(d['stage_ms_per_step'])"
