@@ -135,7 +135,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-int gemm_simt(const rb_gemm_args* a, cudaStream_t stream);
+int gemm_simt(const rb_gemm_args* a, cudaStream_t stream, int lower_only = 0);
 int gemm_tc(const rb_gemm_args* a, cudaStream_t stream);
 Epilogue make_epilogue(const rb_gemm_args* a);
 

@@ -34,6 +34,7 @@ struct SimtParams {
     int64_t sa0, sa1, sb0, sb1, sc0, sc1, sr0, sr1, sna0, snb0;
     int ntaps, k_per_tap; int tap_rows[9]; int64_t a_rows;
     int vec_a, vec_b;
+    int lower_only;          // skip tiles that lie entirely above the diagonal (symmetric trailing updates)
     Epilogue epi;
 };
 
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
     const int tid = threadIdx.x;
     const int tx = tid % NT_N, ty = tid / NT_N;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (p.lower_only && n0 >= m0 + BM) return;
     const int z = blockIdx.z, z0 = z / p.batch1, z1 = z % p.batch1;
     const float* __restrict__ A = p.A + z0 * p.sa0 + z1 * p.sa1;
     const float* __restrict__ B = p.B + z0 * p.sb0 + z1 * p.sb1;
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
     }
 }
 
-int gemm_simt(const rb_gemm_args* a, cudaStream_t stream) {
+int gemm_simt(const rb_gemm_args* a, cudaStream_t stream, int lower_only) {
     RB_REQUIRE(a->dtype_ab == RB_F32, "gemm_simt: operands must be fp32 (got dtype %d)", a->dtype_ab);
     RB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "gemm_simt: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
     SimtParams p;
@@ -245,6 +247,7 @@ int gemm_simt(const rb_gemm_args* a, cudaStream_t stream) {
     }
     p.vec_a = (a->lda % 4 == 0) && (((uintptr_t)a->A) % 16 == 0) && (a->sa0 % 4 == 0) && (a->sa1 % 4 == 0);
     p.vec_b = (a->ldb % 4 == 0) && (((uintptr_t)a->B) % 16 == 0) && (a->sb0 % 4 == 0) && (a->sb1 % 4 == 0);
+    p.lower_only = lower_only;
     p.epi = make_epilogue(a);
     int zdim = batch0 * p.batch1;
     RB_REQUIRE(zdim <= 65535, "gemm_simt: batch %d too large", zdim);

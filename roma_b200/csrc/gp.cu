@@ -342,13 +342,13 @@ __global__ void __launch_bounds__(GP_THREADS) gp_solve_persistent_kernel(const G
 }
 
 static int sub_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int trans_b, float* C, int64_t ldc, int M, int N, int K,
-                    int batch, int64_t stride, cudaStream_t st) {
+                    int batch, int64_t stride, cudaStream_t st, int lower_only = 0) {
     rb_gemm_args g = {};
     g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
     g.dtype_ab = RB_F32; g.dtype_c = RB_F32; g.trans_b = trans_b;
     g.batch0 = batch; g.batch1 = 1; g.sa0 = stride; g.sb0 = stride; g.sc0 = stride; g.sr0 = stride;
     g.ntaps = 1; g.alpha = -1.0f; g.R = C; g.ldr = ldc; g.dtype_r = RB_F32;
-    return gemm_simt(&g, st);
+    return gemm_simt(&g, st, lower_only);
 }
 
 
@@ -361,124 +361,241 @@ static int sub_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, in
 // --------------------------------------------------------------------------------------------------
 constexpr int BB = 128, BBP = BB + 1;
 
-__device__ __forceinline__ void mm32_acc(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float acc[4], int r, int c4) {
-    // acc[0..3] += A[r, 0:32] . B[0:32, c4*4 .. c4*4+3]   (32x32 blocks in shared memory)
-#pragma unroll 8
-    for (int p = 0; p < 32; ++p) {
-        const float a = A[r * lda + p];
-        const float* b = B + p * ldb + c4 * 4;
-        acc[0] = fmaf(a, b[0], acc[0]); acc[1] = fmaf(a, b[1], acc[1]); acc[2] = fmaf(a, b[2], acc[2]); acc[3] = fmaf(a, b[3], acc[3]);
-    }
+constexpr int CB_THREADS = 512;
+constexpr int CB_BUF = 40;                 // floats per broadcast buffer: 32 column entries, 1/pivot, 1/sqrt(pivot), pad
+constexpr int VP = BB + 4;                 // row pitch of L^-1 in shared memory: rows stay 16-byte aligned for float4 access
+constexpr int CB_SMEM_FLOATS = BB * BBP + 3 + BB * VP + 32 * BB + 2 * CB_BUF + BB;
+#ifdef RB_CB_CLK
+__device__ long long g_cb_clk[32];
+#define CBCLK(i) if (threadIdx.x == 0 && blockIdx.x == 0) g_cb_clk[i] = clock64();
+#else
+#define CBCLK(i)
+#endif
+
+__device__ __forceinline__ void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// 1/sqrt(p) of a pivot.  This sits on the serial chain of the whole factorisation, hence MUFU.RSQ and one Newton step
+// (full fp32 accuracy; pivots of K + sigma*I are far from the denormal range) instead of a division and a square root.
+__device__ __forceinline__ float rsqrt_newton(float p) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+    return r * fmaf(-0.5f * p * r, r, 1.5f);
 }
 
-__global__ void __launch_bounds__(256) chol_block128_kernel(float* __restrict__ W, float* __restrict__ inv_ws, int64_t ldw, int64_t stride,
-                                                            int64_t ws_stride, int k, int kb, int bs) {
+// One CTA factors the 128x128 diagonal block in shared memory and forms the inverse of the factor.
+//   factorisation: four 32-column sub-panels.  Sub-panel: one thread per row keeps its 32 entries in registers; for step
+//     j the 32 threads of the diagonal rows publish their column-j entry (double-buffered, one named barrier per step,
+//     column j+1 is published before the rest of step j's updates so that the barrier wait overlaps them), everybody
+//     applies a[c] -= a[j]/p * col[c] and scales a[j] by 1/sqrt(p).  Trailing update inside the block: 4x4 register
+//     tiles over the lower triangle, operands read as float4 from a transposed copy of the sub-panel.
+//   inverse: 32x32 diagonal blocks by forward substitution in registers, then block row by block row
+//     V[bi][0:bi] = -V[bi][bi] (L[bi][0:bi] V[0:bi][0:bi])  as two register-tiled products.
+// History: a fully unrolled first version had 20k instructions and was instruction-fetch bound (664 us per block); a
+// column-at-a-time version with per-element predicates took 105 us; shared-memory wavefronts (one per cycle per SM)
+// and in-order issue behind dependent loads are what the current structure is built around.
+__global__ void __launch_bounds__(CB_THREADS) chol_block128_kernel(float* __restrict__ W, float* __restrict__ inv_ws, int64_t ldw, int64_t stride,
+                                                                   int64_t ws_stride, int k, int kb, int bs) {
     rb::pdl_wait();
-    extern __shared__ float sm128[];
-    float (*S)[BBP] = reinterpret_cast<float (*)[BBP]>(sm128);                    // the block, then its factor L
-    float (*V)[BBP] = reinterpret_cast<float (*)[BBP]>(sm128 + BB * BBP);         // L^-1
-    float (*T)[33] = reinterpret_cast<float (*)[33]>(sm128 + 2 * BB * BBP);       // 32x32 scratch
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ __align__(16) float sm128[];
+    float* S = sm128;                                  // [128][129] the block, then its factor L (lower)
+    float* V = sm128 + ((BB * BBP + 3) & ~3);          // [128][132] L^-1
+    float* PT = V + BB * VP;                           // [32][128]  transposed sub-panel; later the scratch X of the inverse
+    float* buf = PT + 32 * BB;                         // [2][CB_BUF]
+    float* Dinv = buf + 2 * CB_BUF;                    // [128] 1 / L_ii
+    const int tid = threadIdx.x;
     float* Wd = W + (int64_t)blockIdx.x * stride + (int64_t)k * ldw + k;
-    for (int idx = tid; idx < BB * BB; idx += 256) {
-        const int i = idx >> 7, c = idx & 127;
-        float v = 0.f;
-        if (i < bs && c < bs && c <= i) v = __ldcg(Wd + (int64_t)i * ldw + c);
-        if (i == c && i >= bs) v = 1.f;                       // identity padding of a partial block
-        S[i][c] = v; V[i][c] = 0.f;
+    CBCLK(0)
+    {
+        float v[16];
+#pragma unroll 1
+        for (int base = 0; base < BB * BB; base += 16 * CB_THREADS) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int idx = base + u * CB_THREADS + tid, i = idx >> 7, c = idx & 127;
+                v[u] = (i < bs && c < bs && c <= i) ? __ldcg(Wd + (int64_t)i * ldw + c) : ((i == c && i >= bs) ? 1.f : 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int idx = base + u * CB_THREADS + tid, i = idx >> 7, c = idx & 127;
+                S[i * BBP + c] = v[u];
+            }
+        }
+        for (int idx = tid; idx < BB * VP / 4; idx += CB_THREADS) reinterpret_cast<float4*>(V)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    // ---- factorisation: four 32-wide sub-panels, everything in shared memory
-    for (int jb = 0; jb < 4; ++jb) {
-        const int j0 = 32 * jb;
-        if (warp == 0) {                                      // 32x32 diagonal sub-block, one row per lane (shuffles)
-            float r[32];
+    CBCLK(1)
+    for (int j0 = 0; j0 < BB; j0 += 32) {
+        const int nrows = BB - j0;                           // rows of this sub-panel = threads taking part (multiple of 32)
+        if (tid < nrows) {
+            const int row = j0 + tid;
+            float a[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) r[c] = c <= lane ? S[j0 + lane][j0 + c] : 0.f;
+            for (int c = 0; c < 32; ++c) a[c] = S[row * BBP + j0 + c];
+            // Producer/consumer barriers: the diagonal rows (warp 0) publish column j+1 and bar.arrive on FULL[(j+1)&1]
+            // as soon as they have it; the other warps bar.sync on it one step later.  FREE[x] goes the other way
+            // (readers of buffer x are done) so that warp 0 never overwrites a buffer still being read.  Inside warp 0 the
+            // pivot scale travels by shuffle, which keeps shared-memory round trips off the serial chain
+            // (shuffle -> 2 mul -> fma -> rsqrt + Newton -> next shuffle).
+            const bool w0 = tid < 32;
+            float rcur = 0.f;
+            if (w0) {
+                rcur = rsqrt_newton(a[0]);
+                buf[tid] = a[0];
+                if (tid == 0) { buf[32] = rcur * rcur; buf[33] = rcur; Dinv[j0] = rcur; }
+                bar_arrive(1, nrows);
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float d = sqrtf(__shfl_sync(0xffffffffu, r[j], j));
-                float lij = 0.f;
-                if (lane == j) r[j] = d;
-                else if (lane > j) { lij = r[j] / d; r[j] = lij; }
+                const float* bj = buf + (j & 1) * CB_BUF;
+                float* bn = buf + ((j + 1) & 1) * CB_BUF;
+                if (w0) __syncwarp(); else bar_named(1 + (j & 1), nrows);
+                float4 cv[8];
 #pragma unroll
-                for (int c = j + 1; c < 32; ++c) {
-                    const float lcj = __shfl_sync(0xffffffffu, lij, c);
-                    if (c <= lane) r[c] = fmaf(-lij, lcj, r[c]);
+                for (int c4 = (j + 1) / 4; c4 < 8; ++c4) cv[c4] = *reinterpret_cast<const float4*>(bj + 4 * c4);
+                float ip, isq;
+                if (w0) { isq = __shfl_sync(0xffffffffu, rcur, j); ip = isq * isq; }
+                else { ip = bj[32]; isq = bj[33]; }
+                const float t = a[j] * ip;
+                const bool upd = tid > j;
+                if (tid >= j) a[j] *= isq;                    // owner: p / sqrt(p) = sqrt(p)
+                if (j < 31) {
+                    if (w0) {
+                        const float4 c1 = cv[(j + 1) / 4];
+                        const float cj1 = ((j + 1) & 3) == 0 ? c1.x : ((j + 1) & 3) == 1 ? c1.y : ((j + 1) & 3) == 2 ? c1.z : c1.w;
+                        if (upd) a[j + 1] = fmaf(-t, cj1, a[j + 1]);
+                        rcur = rsqrt_newton(a[j + 1]);        // every lane, meaningful in lane j+1 (no divergence)
+                        if (j >= 1) bar_named(3 + ((j + 1) & 1), nrows);
+                        bn[tid] = a[j + 1];
+                        if (tid == j + 1) { bn[32] = rcur * rcur; bn[33] = rcur; Dinv[j0 + j + 1] = rcur; }
+                        bar_arrive(1 + ((j + 1) & 1), nrows);
+                    }
+                    if (upd) {
+#pragma unroll
+                        for (int c4 = (j + 1) / 4; c4 < 8; ++c4) {
+                            const int lo = w0 ? j + 2 : j + 1;        // warp 0 has applied column j+1 already
+                            if (4 * c4 + 0 >= j + 1 && 4 * c4 + 0 >= lo) a[4 * c4 + 0] = fmaf(-t, cv[c4].x, a[4 * c4 + 0]);
+                            if (4 * c4 + 1 >= j + 1 && 4 * c4 + 1 >= lo) a[4 * c4 + 1] = fmaf(-t, cv[c4].y, a[4 * c4 + 1]);
+                            if (4 * c4 + 2 >= j + 1 && 4 * c4 + 2 >= lo) a[4 * c4 + 2] = fmaf(-t, cv[c4].z, a[4 * c4 + 2]);
+                            if (4 * c4 + 3 >= j + 1 && 4 * c4 + 3 >= lo) a[4 * c4 + 3] = fmaf(-t, cv[c4].w, a[4 * c4 + 3]);
+                        }
+                    }
+                    if (!w0 && j < 30) bar_arrive(3 + (j & 1), nrows);
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 32; ++c) S[j0 + lane][j0 + c] = c <= lane ? r[c] : 0.f;
-        }
-        __syncthreads();
-        const int row = j0 + 32 + tid;                        // rows of the block below the sub-panel
-        if (tid < 96 && row < BB) {
-            float a[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) a[c] = S[row][j0 + c];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float x = a[j] / S[j0 + j][j0 + j];
-                a[j] = x;
-#pragma unroll
-                for (int c = j + 1; c < 32; ++c) a[c] = fmaf(-x, S[j0 + c][j0 + j], a[c]);
+            for (int c = 0; c < 32; ++c) {
+                if (tid >= 32 || c <= tid) S[row * BBP + j0 + c] = a[c];
+                PT[c * BB + row] = a[c];
             }
-#pragma unroll
-            for (int c = 0; c < 32; ++c) S[row][j0 + c] = a[c];
         }
         __syncthreads();
-        const int rem = BB - (j0 + 32);                       // trailing part of the block: lower triangle only
-        for (int idx = tid; idx < rem * rem; idx += 256) {
-            const int i = j0 + 32 + idx / rem, c = j0 + 32 + idx % rem;
-            if (c <= i) {
-                float s = 0.f;
+        CBCLK(2 + (j0 >> 5) * 2)
+        // trailing update of the block: C[i][c] -= sum_p L[i][j0+p] L[c][j0+p] over lower-triangular 4x4 tiles
+        const int r0 = j0 + 32, nt = (BB - r0) >> 2, ntiles = nt * (nt + 1) / 2;
+        if (tid < ntiles) {
+            int ti = (int)((sqrtf(8.f * tid + 1.f) - 1.f) * 0.5f);
+            while (ti * (ti + 1) / 2 > tid) --ti;
+            while ((ti + 1) * (ti + 2) / 2 <= tid) ++ti;
+            const int tj = tid - ti * (ti + 1) / 2;
+            const int i0 = r0 + 4 * ti, c0 = r0 + 4 * tj;
+            float acc[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
 #pragma unroll 8
-                for (int p = 0; p < 32; ++p) s = fmaf(S[i][j0 + p], S[c][j0 + p], s);
-                S[i][c] -= s;
+            for (int p = 0; p < 32; ++p) {
+                const float4 av = *reinterpret_cast<const float4*>(PT + p * BB + i0);
+                const float4 bv = *reinterpret_cast<const float4*>(PT + p * BB + c0);
+                const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(aa[x], bb[y], acc[x][y]);
             }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) S[(i0 + x) * BBP + c0 + y] -= acc[x][y];
         }
         __syncthreads();
+        CBCLK(3 + (j0 >> 5) * 2)
     }
-    // ---- inverse of the lower-triangular factor, block-wise: V_bb = L_bb^-1, V_ij = -V_ii (sum_m L_im V_mj)
-    if (tid < 128) {
-        const int b = tid >> 5, j = tid & 31, o = 32 * b;
+    // ---- inverse, diagonal 32x32 blocks: thread = (block, column), forward substitution with the column in registers
+    if (tid < BB) {
+        const int o = tid & ~31, jj = tid & 31;
         float x[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            float s = i == j ? 1.f : 0.f;
+            const float* Lr = S + (o + i) * BBP + o;
+            float s0 = i == jj ? 1.f : 0.f, s1 = 0.f;
 #pragma unroll
-            for (int p = 0; p < 32; ++p)
-                if (p < i) s = fmaf(-S[o + i][o + p], x[p], s);
-            x[i] = i >= j ? s / S[o + i][o + i] : 0.f;
+            for (int p = 0; p < i; ++p) {
+                if (p & 1) s1 = fmaf(-Lr[p], x[p], s1);
+                else s0 = fmaf(-Lr[p], x[p], s0);
+            }
+            x[i] = i >= jj ? (s0 + s1) * Dinv[o + i] : 0.f;
+            V[(o + i) * VP + o + jj] = x[i];
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) V[o + i][o + j] = x[i];
     }
     __syncthreads();
-    const int r = tid >> 3, c4 = tid & 7;
-    for (int d = 1; d < 4; ++d) {
-        for (int bi = d; bi < 4; ++bi) {
-            const int bj = bi - d;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int m = bj; m < bi; ++m) mm32_acc(&S[32 * bi][32 * m], BBP, &V[32 * m][32 * bj], BBP, acc, r, c4);
-            __syncthreads();
+    CBCLK(10)
+    // ---- inverse, off-diagonal: block row bi,  X = L[bi][0:bi] V[0:bi][0:bi]  then  V[bi][0:bi] = -V[bi][bi] X
+    for (int bi = 1; bi < 4; ++bi) {
+        const int ctiles = 8 * bi, ntile = 8 * ctiles;         // 4x4 tiles: 8 tile rows x 8*bi tile columns
+        const int ct = tid % ctiles, rt = tid / ctiles, c0 = 4 * ct, rr = 32 * bi + 4 * rt;
+        if (tid < ntile) {
+            float acc[4][4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) T[r][c4 * 4 + q] = acc[q];
-            __syncthreads();
-            float acc2[4] = {0.f, 0.f, 0.f, 0.f};
-            mm32_acc(&V[32 * bi][32 * bi], BBP, &T[0][0], 33, acc2, r, c4);
+            for (int x = 0; x < 4; ++x)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) V[32 * bi + r][32 * bj + c4 * 4 + q] = -acc2[q];
-            __syncthreads();
+                for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+#pragma unroll 4
+            for (int p = c0 & ~31; p < 32 * bi; ++p) {          // V[p][c] = 0 above the diagonal block of column c
+                const float4 bv = *reinterpret_cast<const float4*>(V + p * VP + c0);
+                const float aa[4] = {S[rr * BBP + p], S[(rr + 1) * BBP + p], S[(rr + 2) * BBP + p], S[(rr + 3) * BBP + p]};
+                const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(aa[x], bb[y], acc[x][y]);
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x) *reinterpret_cast<float4*>(PT + (4 * rt + x) * BB + c0) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
         }
+        __syncthreads();
+        if (tid < ntile) {
+            float acc[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+            const float* Vd = V + rr * VP + 32 * bi;            // rows of the diagonal block V[bi][bi] (lower triangular)
+#pragma unroll 4
+            for (int q = 0; q < 4 * rt + 4; ++q) {
+                const float4 bv = *reinterpret_cast<const float4*>(PT + q * BB + c0);
+                const float aa[4] = {Vd[q], Vd[VP + q], Vd[2 * VP + q], Vd[3 * VP + q]};
+                const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(aa[x], bb[y], acc[x][y]);
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x) *reinterpret_cast<float4*>(V + (rr + x) * VP + c0) = make_float4(-acc[x][0], -acc[x][1], -acc[x][2], -acc[x][3]);
+        }
+        __syncthreads();
     }
+    CBCLK(11)
     // ---- write back: L in place (lower triangle), L^-1 to the workspace as a dense [128][128] block
     float* Vout = inv_ws + (int64_t)blockIdx.x * ws_stride + (int64_t)kb * BB * BB;
-    for (int idx = tid; idx < BB * BB; idx += 256) {
+    for (int idx = tid; idx < BB * BB; idx += CB_THREADS) {
         const int i = idx >> 7, c = idx & 127;
-        if (i < bs && c < bs && c <= i) Wd[(int64_t)i * ldw + c] = S[i][c];
-        Vout[idx] = V[i][c];
+        if (i < bs && c < bs && c <= i) Wd[(int64_t)i * ldw + c] = S[i * BBP + c];
+        Vout[idx] = V[i * VP + c];
     }
+    CBCLK(12)
 }
 
 static int plain_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int trans_b, float* C, int64_t ldc, int M, int N, int K,
@@ -497,7 +614,7 @@ static int gp_solve_block128(const rb_gp_solve_args* a, cudaStream_t st) {
     float* W = a->W;
     float* ws = (float*)a->workspace;
     static bool configured = false;
-    const size_t smem = (size_t)(2 * BB * BBP + 32 * 33) * sizeof(float);
+    const size_t smem = (size_t)CB_SMEM_FLOATS * sizeof(float);
     if (!configured) {
         RB_REQUIRE(cudaFuncSetAttribute(chol_block128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
                    "gp_solve: cannot reserve %zu bytes of shared memory", smem);
@@ -505,7 +622,7 @@ static int gp_solve_block128(const rb_gp_solve_args* a, cudaStream_t st) {
     }
     for (int kb = 0; kb < nblk; ++kb) {
         const int k = kb * BB, bs = n - k < BB ? n - k : BB;
-        rb::launch_pdl(chol_block128_kernel, dim3(a->batch), dim3(256), smem, st, W, ws, a->ldw, a->stride, ws_stride, k, kb, bs);
+        rb::launch_pdl(chol_block128_kernel, dim3(a->batch), dim3(CB_THREADS), smem, st, W, ws, a->ldw, a->stride, ws_stride, k, kb, bs);
         if (check_launch("chol_block128")) return 1;
         const int below = total - (k + bs);
         if (below > 0) {
@@ -514,7 +631,7 @@ static int gp_solve_block128(const rb_gp_solve_args* a, cudaStream_t st) {
             const int nt = n - (k + bs);
             if (nt > 0) {
                 float* Tm = W + (int64_t)(k + bs) * a->ldw + (k + bs);
-                if (sub_gemm(P, a->ldw, P, a->ldw, 0, Tm, a->ldw, below, nt, bs, a->batch, a->stride, st)) return 1;
+                if (sub_gemm(P, a->ldw, P, a->ldw, 0, Tm, a->ldw, below, nt, bs, a->batch, a->stride, st, 1)) return 1;
             }
         }
     }
@@ -534,6 +651,10 @@ static int gp_solve_block128(const rb_gp_solve_args* a, cudaStream_t st) {
 }  // namespace rb
 
 using namespace rb;
+
+#ifdef RB_CB_CLK
+extern "C" int romab200_debug_clk(long long* out) { return (int)cudaMemcpyFromSymbol(out, rb::g_cb_clk, sizeof(long long) * 32); }
+#endif
 
 extern "C" int romab200_gp_solve(const rb_gp_solve_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -581,7 +702,7 @@ extern "C" int romab200_gp_solve(const rb_gp_solve_args* a, void* stream) {
         if (nt > 0) {
             float* P = W + (int64_t)(k + bs) * a->ldw + k;           // panel rows below the block
             float* T = W + (int64_t)(k + bs) * a->ldw + (k + bs);    // trailing matrix
-            if (sub_gemm(P, a->ldw, P, a->ldw, 0, T, a->ldw, total - (k + bs), nt, bs, a->batch, a->stride, st)) return 1;
+            if (sub_gemm(P, a->ldw, P, a->ldw, 0, T, a->ldw, total - (k + bs), nt, bs, a->batch, a->stride, st, 1)) return 1;   // only the lower triangle is ever read
         }
     }
     // backward substitution: X^T L = Y^T on rows n .. n+nrhs

@@ -51,9 +51,9 @@ class Engine:
         self._const: Dict[tuple, torch.Tensor] = {}
         self.debug: Optional[dict] = None        # set to {} to keep stage tensors (tests)
         self.use_flash_attn = True               # fused tcgen05 attention in the 16-bit modes (else QK^T / softmax / PV GEMMs)
-        self.gp_algo = 0                         # 0: 32-wide launch chain (fastest measured: 3.4 ms for two 1600^2 problems),
-                                                 # 1: one cooperative persistent kernel (4.0 ms), 2: 128-wide blocks factored in shared
-                                                 # memory + explicit block inverses (8.8 ms: the in-smem block kernel is latency-bound)
+        self.gp_algo = 2                         # 2: 128-wide blocks factored in shared memory + explicit block inverses, the rest
+                                                 # K=128 GEMMs (13 dependent steps); 0: 32-wide launch chain (50 steps);
+                                                 # 1: one cooperative persistent kernel.  Timings in DESIGN.md.
         self.overlap_cnn = True                  # VGG/proj branch on a side stream, overlapping ViT / GP / decoder
         self.gp_tensor_core = True               # all-pairs CosKernel on tcgen05 (split-fp16 operands) in the 16-bit modes
         self.fused_c144 = True                   # stride-2 refiner blocks as one fused DW + tcgen05-PW kernel

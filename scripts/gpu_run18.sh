@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python bench.py --precision fp16 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_fp16.json 2> gpurun_out/bench_fp16.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_fp16.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['eager_ms_per_step'])"; tail -n 3 gpurun_out/bench_fp16.err
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -p no:cacheprovider -k "gp_solve" 2>&1 | grep -E "Error|passed|failed|^FAILED" | head
+timeout 60 python scripts/gp_clk.py
+timeout 60 python scripts/gp_profile.py 2
