@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ROMAB200_ABI_VERSION 1
+#define ROMAB200_ABI_VERSION 2
 
 enum rb_dtype { RB_F32 = 0, RB_F16 = 1, RB_BF16 = 2 };
 enum rb_act { RB_ACT_NONE = 0, RB_ACT_RELU = 1, RB_ACT_GELU = 2 };
@@ -198,11 +198,12 @@ typedef struct {
 int romab200_dwconv5x5_relu(const rb_dwconv_args* args, void* stream);
 
 /* Fused thin-map ConvRefiner block (C = 24, stride-1 maps): out = PW(ReLU(BN(DW5x5(in)))) in one pass.
- * in/out: channels-last 16-bit maps [batch, h, w, ld] (in != out); dw_weight [25][ldw] fp32 tap-major (BN folded),
- * pw_weight [c][c] fp32 row-major.  (create_block, matcher.py:92-122) */
+ * in/out: channels-last 16-bit maps [batch, h, w, ld] (in != out); dw_weight [25][ldw] fp32 tap-major (BN folded), device.
+ * pw_weight_host [c][c] fp32 row-major and pw_bias_host [c] are HOST arrays: the pointwise weights are passed to the
+ * kernel as launch parameters (constant bank), they are read during this call only.  (create_block, matcher.py:92-122) */
 typedef struct {
     const void* in; void* out; int64_t ld; const float* dw_weight; int64_t ldw; const float* dw_bias;
-    const float* pw_weight; const float* pw_bias; int32_t batch, h, w, c; int32_t dtype;
+    const float* pw_weight_host; const float* pw_bias_host; int32_t batch, h, w, c; int32_t dtype;
 } rb_refiner_block_small_args;
 int romab200_refiner_block_small(const rb_refiner_block_small_args* args, void* stream);
 

@@ -137,6 +137,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 int gemm_simt(const rb_gemm_args* a, cudaStream_t stream, int lower_only = 0);
 int gemm_tc(const rb_gemm_args* a, cudaStream_t stream);
+int dwconv_tma(const rb_dwconv_args* a, cudaStream_t stream);     // dwconv_tma.cu: TMA-fed persistent depthwise kernel (16-bit maps)
 Epilogue make_epilogue(const rb_gemm_args* a);
 
 }  // namespace rb

@@ -426,21 +426,26 @@ __global__ void __launch_bounds__(128) dwconv5x5_relu_h2_kernel(const T* __restr
 // largest tensors of the path (1.5 M pixels at 864^2) and far too thin for a tensor-core tile, so this is a
 // CUDA-core kernel: a 16x16 pixel tile (+2 halo) is staged in shared memory, the depthwise stage runs
 // channel-pair x row strips with its 50 filter taps in registers, the pointwise stage runs one pixel per
-// thread against broadcast weights.
+// thread.  The pointwise weights travel as a KERNEL PARAMETER (2.4 KB): every use is an FFMA with a
+// constant-bank operand, so the stage needs no shared-memory traffic and no weight registers.  (ncu on the
+// previous version, which broadcast the weights from shared memory with LDS.128: LSU wavefronts at 77 % of
+// peak, a third of them bank conflicts of the depthwise reads, FMA pipe 37 % busy.)
 // --------------------------------------------------------------------------------------------------
+template <int C>
+struct SmallPw { float w[C][C]; float b[C]; };        // w[co][ci]
+
 template <typename T, int C>
 __global__ void __launch_bounds__(256) refiner_block_small_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t ld,
                                                                   const float* __restrict__ dw_w, int64_t ldw, const float* __restrict__ dw_b,
-                                                                  const float* __restrict__ pw_w, const float* __restrict__ pw_b,
-                                                                  int H, int W, int tiles_x) {
+                                                                  const __grid_constant__ SmallPw<C> pw, int H, int W, int tiles_x) {
     rb::pdl_wait();
     constexpr int TS = 16, IN = TS + 4, CP = C / 2;
-    constexpr int PS = C + 2;                 // input pixel stride in halves (odd number of 32-bit words: conflict-free)
+    constexpr int PS = C + 2;                 // input pixel stride in halves (odd number of 32-bit words)
+    constexpr int RS = IN * PS + 16;          // input row stride in halves: 268 words = 12 mod 32, so the (channel pair, row) lanes
+                                              // of a warp, 12 consecutive words per row, fall into 32 distinct banks
     constexpr int MS = C + 1;                 // mid pixel stride in floats
-    __shared__ __align__(16) T tile[IN * IN * PS];
+    __shared__ __align__(16) T tile[IN * RS];
     __shared__ float mid[TS * TS * MS];
-    __shared__ __align__(16) float2 wpw[C * CP];      // [ci][co pair] = (W[2p][ci], W[2p+1][ci]): operands of the packed FFMA2
-    __shared__ float2 bpw[CP];
     const int tid = threadIdx.x;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, b = blockIdx.y;
     const int x0 = tx * TS, y0 = ty * TS;
@@ -463,16 +468,12 @@ __global__ void __launch_bounds__(256) refiner_block_small_kernel(const T* __res
             const int i = tid + k * 256;
             if (i < NV) {
                 const int pix = i / VPP, v = i - pix * VPP;
-                uint32_t* dst = reinterpret_cast<uint32_t*>(&tile[pix * PS + 8 * v]);      // pixel stride 52 B: 4-byte aligned
+                const int py = pix / IN, px = pix - py * IN;
+                uint32_t* dst = reinterpret_cast<uint32_t*>(&tile[py * RS + px * PS + 8 * v]);      // pixel stride 52 B: 4-byte aligned
                 dst[0] = vals[k].x; dst[1] = vals[k].y; dst[2] = vals[k].z; dst[3] = vals[k].w;
             }
         }
     }
-    for (int i = tid; i < C * CP; i += 256) {
-        const int ci = i / CP, pr = i - ci * CP;
-        wpw[i] = make_float2(pw_w[(2 * pr) * C + ci], pw_w[(2 * pr + 1) * C + ci]);
-    }
-    if (tid < CP) bpw[tid] = make_float2(pw_b[2 * tid], pw_b[2 * tid + 1]);
     // ---- depthwise: thread = (channel pair, output row); taps in registers, packed FFMA2
     const int cp = tid % CP, row = tid / CP;
     float2 wv[25];
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(256) refiner_block_small_kernel(const T* __res
 #pragma unroll
             for (int px = 0; px < IN; ++px) {
                 T pr[2];
-                *reinterpret_cast<uint32_t*>(pr) = *reinterpret_cast<const uint32_t*>(&tile[((row + ky) * IN + px) * PS + 2 * cp]);
+                *reinterpret_cast<uint32_t*>(pr) = *reinterpret_cast<const uint32_t*>(&tile[(row + ky) * RS + px * PS + 2 * cp]);
                 const float2 v = make_float2(to_f(pr[0]), to_f(pr[1]));
 #pragma unroll
                 for (int kx = 0; kx < 5; ++kx) {
@@ -509,28 +510,22 @@ __global__ void __launch_bounds__(256) refiner_block_small_kernel(const T* __res
         }
     }
     __syncthreads();
-    // ---- pointwise: thread = pixel, two output channels per FFMA2 against broadcast weights
+    // ---- pointwise: thread = pixel; weights are constant-bank operands of the FFMAs
     const int py = tid / TS, px = tid - py * TS;
     const int yy = y0 + py, xx = x0 + px;
     if (yy >= H || xx >= W) return;
-    float2 o[CP];
+    float av[C];
 #pragma unroll
-    for (int pr = 0; pr < CP; ++pr) o[pr] = bpw[pr];
-#pragma unroll
-    for (int ci = 0; ci < C; ++ci) {
-        const float av = mid[tid * MS + ci];
-        const float2 a2 = make_float2(av, av);
-#pragma unroll
-        for (int pr = 0; pr < CP; pr += 2) {
-            const float4 w4 = *reinterpret_cast<const float4*>(&wpw[ci * CP + pr]);     // two channel pairs per LDS.128
-            o[pr] = __ffma2_rn(make_float2(w4.x, w4.y), a2, o[pr]);
-            o[pr + 1] = __ffma2_rn(make_float2(w4.z, w4.w), a2, o[pr + 1]);
-        }
-    }
-    T* op = out + ((int64_t)b * H * W + (int64_t)yy * W + xx) * ld;
+    for (int ci = 0; ci < C; ++ci) av[ci] = mid[tid * MS + ci];
     T res[C];
 #pragma unroll
-    for (int pr = 0; pr < CP; ++pr) { res[2 * pr] = from_f<T>(o[pr].x); res[2 * pr + 1] = from_f<T>(o[pr].y); }
+    for (int co = 0; co < C; ++co) {
+        float o = pw.b[co];
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) o = fmaf(pw.w[co][ci], av[ci], o);
+        res[co] = from_f<T>(o);
+    }
+    T* op = out + ((int64_t)b * H * W + (int64_t)yy * W + xx) * ld;
 #pragma unroll
     for (int v = 0; v < C / 8; ++v) *reinterpret_cast<uint4*>(op + 8 * v) = *reinterpret_cast<const uint4*>(&res[8 * v]);
 }
@@ -780,10 +775,7 @@ extern "C" int romab200_dwconv5x5_relu(const rb_dwconv_args* a, void* stream) {
     const int cpad = (a->c + 7) & ~7;
     if (a->dtype != RB_F32 && a->ldi % 8 == 0 && a->ldo % 2 == 0 && a->ldi >= cpad && a->ldo >= cpad &&
         ((uintptr_t)a->in) % 16 == 0 && ((uintptr_t)a->out) % 4 == 0) {
-        dim3 grid2(tiles_x * tiles_y, (a->c + 63) / 64, a->batch);
-        if (a->dtype == RB_F16) rb::launch_pdl(dwconv5x5_relu_h2_kernel<__half>, dim3(grid2), dim3(128), 0, st, (const __half*)a->in, (__half*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
-        else rb::launch_pdl(dwconv5x5_relu_h2_kernel<__nv_bfloat16>, dim3(grid2), dim3(128), 0, st, (const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
-        return check_launch("dwconv5x5_relu");
+        return dwconv_tma(a, st);
     }
     if (a->dtype == RB_F32) rb::launch_pdl(dwconv5x5_relu_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)a->in, (float*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
     else if (a->dtype == RB_F16) rb::launch_pdl(dwconv5x5_relu_kernel<__half>, dim3(grid), dim3(256), 0, st, (const __half*)a->in, (__half*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
@@ -799,12 +791,18 @@ extern "C" int romab200_refiner_block_small(const rb_refiner_block_small_args* a
     int tiles_x = (a->w + 15) / 16, tiles_y = (a->h + 15) / 16;
     dim3 grid(tiles_x * tiles_y, a->batch);
     RB_REQUIRE(grid.y <= 65535, "refiner_block_small: batch too large");
+    RB_REQUIRE(a->pw_weight_host && a->pw_bias_host, "refiner_block_small: the pointwise weights must be given as HOST arrays (they are passed as kernel parameters)");
+    SmallPw<24> pw;
+    for (int co = 0; co < 24; ++co) {
+        for (int ci = 0; ci < 24; ++ci) pw.w[co][ci] = a->pw_weight_host[co * 24 + ci];
+        pw.b[co] = a->pw_bias_host[co];
+    }
     if (a->dtype == RB_F16)
         rb::launch_pdl(refiner_block_small_kernel<__half, 24>, dim3(grid), dim3(256), 0, st, (const __half*)a->in, (__half*)a->out, a->ld, a->dw_weight, a->ldw, a->dw_bias,
-                                                                     a->pw_weight, a->pw_bias, a->h, a->w, tiles_x);
+                       pw, a->h, a->w, tiles_x);
     else
         rb::launch_pdl(refiner_block_small_kernel<__nv_bfloat16, 24>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ld, a->dw_weight,
-                                                                            a->ldw, a->dw_bias, a->pw_weight, a->pw_bias, a->h, a->w, tiles_x);
+                       a->ldw, a->dw_bias, pw, a->h, a->w, tiles_x);
     return check_launch("refiner_block_small");
 }
 

@@ -2,9 +2,10 @@
 // (create_block, romatch/models/matcher.py:92-122) in ONE kernel: the activation map is read once and written once.
 // Un-fused, this block is a depthwise kernel plus a GEMM that together move the 107 MB map four times and spend most
 // of their time in per-tile overheads; here
-//   * 9 producer warps stage an 8x16 pixel tile (+2 halo) in shared memory and run the depthwise stage on the CUDA
-//     cores (channel pairs, packed FFMA2, filter taps in registers for the whole persistent kernel), writing the
-//     ReLU'd 128 x 144 result straight into the 128B-swizzled K-major layout of a UMMA A operand;
+//   * 1 thread TMA-loads the 12x20 pixel input window of an 8x16 tile (4-D tensor map over [B,H,W,C]: the image border
+//     is the map's out-of-bounds zero fill, no address arithmetic, no registers);
+//   * 9 depthwise warps run the 5x5 stage on the CUDA cores (channel pairs, packed FFMA2) and write the ReLU'd
+//     128 x 144 result straight into the 128B-swizzled K-major layout of a UMMA A operand;
 //   * 1 thread issues 9 tcgen05.mma (M=128, N=144, K=16) against the pointwise weights, which were TMA-loaded into
 //     shared memory once and stay resident;
 //   * 4 epilogue warps read the fp32 accumulator from TMEM (double-buffered), add the bias and store 16-bit rows.
@@ -39,6 +40,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
@@ -88,6 +95,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 }  // namespace fz
 
+#ifdef RB_FZ_CLK
+__device__ long long g_fz_clk[64];
+#define FZCLK(var) const long long var = clock64();
+#else
+#define FZCLK(var)
+#endif
+
 struct FusedParams {
     const void* in; void* out; int64_t ld;
     const float* dw_w; int64_t ldw; const float* dw_b; const float* pw_b;
@@ -96,7 +110,7 @@ struct FusedParams {
 
 constexpr int FZ_C = 144, FZ_CP = 72, FZ_TH = 8, FZ_TW = 16, FZ_IH = 12, FZ_IW = 20;
 constexpr int FZ_DW_THREADS = 288;                    // 72 channel pairs x 4 row groups
-constexpr int FZ_THREADS = 32 + 128 + FZ_DW_THREADS;  // warp 0: TMA + MMA, warps 1-4: epilogue, warps 5-13: depthwise
+constexpr int FZ_THREADS = 32 + 128 + FZ_DW_THREADS + 32;  // warp 0: weights + MMA, warps 1-4: epilogue, warps 5-13: depthwise, warp 14: input TMA
 constexpr int FZ_IN_BYTES = FZ_IH * FZ_IW * FZ_C * 2;              // 69120
 constexpr int FZ_A_BYTES = 3 * 128 * 128;                          // 49152: 3 k-blocks of 64 channels, 128 pixel rows
 constexpr int FZ_B_KB = FZ_C * 128;                                // 18432 per k-block
@@ -105,7 +119,7 @@ constexpr int FZ_W_BYTES = 25 * FZ_C * 4;                          // depthwise 
 constexpr int FZ_SMEM = FZ_A_BYTES + FZ_B_BYTES + FZ_IN_BYTES + FZ_W_BYTES + 1024 + 1024;
 
 template <typename T>
-__global__ void __launch_bounds__(FZ_THREADS, 1) refiner_block_c144_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParams p) {
+__global__ void __launch_bounds__(FZ_THREADS, 1) refiner_block_c144_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_in, const FusedParams p) {
     rb::pdl_wait();
     using namespace fz;
     extern __shared__ uint8_t smem_raw[];
@@ -120,13 +134,16 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) refiner_block_c144_kernel(const
     uint64_t* a_empty = bars + 2;       // MMAs that read it retired
     uint64_t* t_full = bars + 3;        // [2] accumulator ready
     uint64_t* t_empty = bars + 5;       // [2] accumulator drained (4 warp arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-    float* s_bias = reinterpret_cast<float*>(bars + 8);     // [144]
+    uint64_t* in_full = bars + 7;       // input window landed (TMA transaction bytes)
+    uint64_t* in_empty = bars + 8;      // depthwise warps have read it (9 warp arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* s_bias = reinterpret_cast<float*>(bars + 10);    // [144]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1); mbar_init(a_full, FZ_DW_THREADS / 32); mbar_init(a_empty, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+        mbar_init(in_full, 1); mbar_init(in_empty, FZ_DW_THREADS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -198,6 +215,18 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) refiner_block_c144_kernel(const
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[acc]);
         }
+    } else if (warp == 14) {
+        // ===== input loader: one TMA box per tile, re-armed as soon as the depthwise warps have read the previous window =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+                const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+                if (it > 0) mbar_wait(in_empty, (it - 1) & 1);
+                mbar_expect_tx(in_full, FZ_IN_BYTES);
+                tma_load_4d(sIn, &map_in, in_full, 0, tx * FZ_TW - 2, ty * FZ_TH - 2, img);
+            }
+        }
     } else {
         // ===== depthwise producers: thread = (channel pair, 2 output rows) =====
         const int t = threadIdx.x - 160;                   // 0 .. 287
@@ -207,35 +236,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) refiner_block_c144_kernel(const
         const int kb = cp >> 5, chunk = (cp & 31) >> 2, inb = (cp & 3) * 4;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
-            const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-            const int y0 = ty * FZ_TH, x0 = tx * FZ_TW;
-            const T* inb_img = (const T*)p.in + (int64_t)img * p.H * p.W * p.ld;
-            asm volatile("bar.sync 2, %0;" ::"n"(FZ_DW_THREADS) : "memory");       // everyone finished reading the previous input tile
-            {
-                constexpr int VPP = FZ_C / 8, NV = FZ_IH * FZ_IW * VPP, PER = (NV + FZ_DW_THREADS - 1) / FZ_DW_THREADS;   // 4320 / 288 = 15
-                constexpr int BATCH = 8;                   // loads in flight per thread (register budget)
-#pragma unroll
-                for (int k0 = 0; k0 < PER; k0 += BATCH) {
-                    uint4 vals[BATCH];
-#pragma unroll
-                    for (int k = 0; k < BATCH; ++k) {
-                        const int i = t + (k0 + k) * FZ_DW_THREADS;
-                        const int pix = i / VPP, v = i - pix * VPP;
-                        const int iy = pix / FZ_IW, ix = pix - iy * FZ_IW;
-                        const int yy = y0 + iy - 2, xx = x0 + ix - 2;
-                        vals[k] = make_uint4(0u, 0u, 0u, 0u);
-                        if (k0 + k < PER && i < NV && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-                            vals[k] = *reinterpret_cast<const uint4*>(inb_img + (uint32_t)((yy * p.W + xx) * (int)p.ld + 8 * v));
-                    }
-#pragma unroll
-                    for (int k = 0; k < BATCH; ++k) {
-                        const int i = t + (k0 + k) * FZ_DW_THREADS;
-                        if (k0 + k < PER && i < NV) reinterpret_cast<uint4*>(sIn)[i] = vals[k];
-                    }
-                }
-            }
-            asm volatile("bar.sync 2, %0;" ::"n"(FZ_DW_THREADS) : "memory");
+            FZCLK(t0)
+            mbar_wait(in_full, it & 1);
+            FZCLK(t1)
             // filter taps: re-read from shared memory per tile so that they are not live during the load phase
             float2 wv[25];
 #pragma unroll
@@ -265,7 +268,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) refiner_block_c144_kernel(const
                     }
                 }
             }
-            mbar_wait(a_empty, (it & 1) ^ 1);              // the MMAs of the previous tile no longer read sA
+            FZCLK(t2)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(in_empty);          // this warp's reads of the input window are done
+            mbar_wait(a_empty, (it & 1) ^ 1);
+            FZCLK(t3)              // the MMAs of the previous tile no longer read sA
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
 #pragma unroll
@@ -278,6 +285,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) refiner_block_c144_kernel(const
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full);
+#ifdef RB_FZ_CLK
+            if (blockIdx.x == 0 && lane == 0) { const long long t4 = clock64(); long long* g = g_fz_clk + (warp - 5) * 5; g[0] += t1 - t0; g[1] += t2 - t1; g[2] += t3 - t2; g[3] += t4 - t3; g[4] += 1; }
+#endif
         }
     }
     tc_fence_before();
@@ -291,6 +301,13 @@ typedef CUresult (*EncodeTiledFnFz)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 }  // namespace rb
 
 using namespace rb;
+
+#ifdef RB_FZ_CLK
+extern "C" int romab200_debug_fzclk(long long* out, int reset) {
+    if (reset) { long long z[64] = {0}; return (int)cudaMemcpyToSymbol(rb::g_fz_clk, z, sizeof(z)); }
+    return (int)cudaMemcpyFromSymbol(out, rb::g_fz_clk, sizeof(long long) * 64);
+}
+#endif
 
 extern "C" int romab200_refiner_block_c144(const rb_refiner_block_c144_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -316,6 +333,17 @@ extern "C" int romab200_refiner_block_c144(const rb_refiner_block_c144_args* a, 
                      dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RB_REQUIRE(r == CUDA_SUCCESS, "refiner_block_c144: cuTensorMapEncodeTiled failed with %d", (int)r);
+    CUtensorMap map_in;          // activation [B, H, W, C] with pitch ld: box = 12 x 20 pixels x 144 channels, borders zero-filled
+    {
+        cuuint64_t d4[4] = {(cuuint64_t)FZ_C, (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->batch};
+        cuuint64_t s4[3] = {(cuuint64_t)a->ld * 2, (cuuint64_t)a->w * a->ld * 2, (cuuint64_t)a->h * a->w * a->ld * 2};
+        cuuint32_t b4[4] = {(cuuint32_t)FZ_C, (cuuint32_t)FZ_IW, (cuuint32_t)FZ_IH, 1};
+        cuuint32_t e4[4] = {1, 1, 1, 1};
+        CUresult r4 = enc(&map_in, a->dtype == RB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a->in),
+                          d4, s4, b4, e4, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RB_REQUIRE(r4 == CUDA_SUCCESS, "refiner_block_c144: cuTensorMapEncodeTiled (input) failed with %d", (int)r4);
+    }
     FusedParams p;
     p.in = a->in; p.out = a->out; p.ld = a->ld; p.dw_w = a->dw_weight; p.ldw = a->ldw; p.dw_b = a->dw_bias; p.pw_b = a->pw_bias;
     p.batch = a->batch; p.H = a->h; p.W = a->w; p.tiles_x = (a->w + FZ_TW - 1) / FZ_TW; p.tiles_y = (a->h + FZ_TH - 1) / FZ_TH;
@@ -329,11 +357,11 @@ extern "C" int romab200_refiner_block_c144(const rb_refiner_block_c144_args* a, 
     if (a->dtype == RB_F16) {
         static bool cfg = false;
         if (!cfg) { RB_REQUIRE(cudaFuncSetAttribute(refiner_block_c144_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM) == cudaSuccess, "refiner_block_c144: smem attribute"); cfg = true; }
-        rb::launch_pdl(refiner_block_c144_kernel<__half>, dim3(grid), dim3(FZ_THREADS), FZ_SMEM, st, map, p);
+        rb::launch_pdl(refiner_block_c144_kernel<__half>, dim3(grid), dim3(FZ_THREADS), FZ_SMEM, st, map, map_in, p);
     } else {
         static bool cfg = false;
         if (!cfg) { RB_REQUIRE(cudaFuncSetAttribute(refiner_block_c144_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM) == cudaSuccess, "refiner_block_c144: smem attribute"); cfg = true; }
-        rb::launch_pdl(refiner_block_c144_kernel<__nv_bfloat16>, dim3(grid), dim3(FZ_THREADS), FZ_SMEM, st, map, p);
+        rb::launch_pdl(refiner_block_c144_kernel<__nv_bfloat16>, dim3(grid), dim3(FZ_THREADS), FZ_SMEM, st, map, map_in, p);
     }
     return check_launch("refiner_block_c144");
 }

@@ -386,7 +386,7 @@ class Engine:
             # thin stride-1 maps: one fused DW5x5+ReLU+PW kernel per block, ping-ponging between the two buffers
             for blk in R["blocks"]:
                 call("romab200_refiner_block_small", "rb_refiner_block_small_args", **{"in": d}, out=t, ld=cp, dw_weight=blk["dw_w"],
-                     ldw=cp, dw_bias=blk["dw_b"], pw_weight=blk["pw_w32"], pw_bias=blk["pw_b"], batch=D, h=h, w=w, c=c, dtype=self.dt)
+                     ldw=cp, dw_bias=blk["dw_b"], pw_weight_host=blk["pw_w_host"].data_ptr(), pw_bias_host=blk["pw_b_host"].data_ptr(), batch=D, h=h, w=w, c=c, dtype=self.dt)
                 d, t = t, d
         elif c == 144 and self.dtype != torch.float32 and self.fused_c144:
             # stride-2 maps: depthwise stage on the CUDA cores feeding a tcgen05 pointwise GEMM inside one kernel

@@ -142,7 +142,9 @@ class PackedWeights:
                 pw_w=_mat(pw, self.dtype, self.device, pitch=cp),
                 pw_b=_vec(sd[f"{q}.3.bias"], self.device),
                 # thin maps (C = 24) run the fused CUDA-core block: fp32 copy of the compute-dtype-rounded weights
-                pw_w32=pw.to(self.dtype).float().contiguous().to(self.device) if c <= 32 else None,
+                # thin maps: the fused block kernel takes its pointwise weights as launch parameters, i.e. from host memory
+                pw_w_host=pw.to(self.dtype).float().contiguous().cpu() if c <= 32 else None,
+                pw_b_host=sd[f"{q}.3.bias"].float().contiguous().cpu() if c <= 32 else None,
             ))
         ow = torch.zeros(3, cp)
         ow[:, :c] = sd[f"{p}.out_conv.weight"].float().flatten(1)

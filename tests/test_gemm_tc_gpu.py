@@ -145,8 +145,9 @@ def test_refiner_block_small_fused_vs_unfused(dt):
     xi = x.permute(0, 2, 3, 1).contiguous()
     out = torch.zeros(B, H, W, C, dtype=dt, device=DEV)
     dwt = dw.reshape(C, 25).t().contiguous()
+    pw_host, pb_host = pw.float().cpu().contiguous(), pb.cpu().contiguous()       # host arrays: they travel as kernel parameters
     call("romab200_refiner_block_small", "rb_refiner_block_small_args", **{"in": xi}, out=out, ld=C, dw_weight=dwt, ldw=C, dw_bias=db,
-         pw_weight=pw.float().contiguous(), pw_bias=pb, batch=B, h=H, w=W, c=C, dtype=CODE[dt])
+         pw_weight_host=pw_host.data_ptr(), pw_bias_host=pb_host.data_ptr(), batch=B, h=H, w=W, c=C, dtype=CODE[dt])
     close(out, ref, 6e-2 if dt == torch.bfloat16 else 8e-3)
 
 
@@ -181,3 +182,22 @@ def test_refiner_block_c144_fused(dt, B, H, W):
          pw_weight=pw.contiguous(), ld_pw=C, pw_bias=pb, batch=B, h=H, w=W, c=C, dtype=CODE[dt])
     torch.cuda.synchronize()
     close(out, ref, 1.5e-1 if dt == torch.bfloat16 else 2e-2)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,C,H,W", [(2, 150, 19, 37), (1, 64, 8, 16), (2, 569, 54, 54), (1, 70, 5, 3)])
+def test_dwconv_16bit_tma(dt, B, C, H, W):
+    """TMA-fed depthwise 5x5 + ReLU on 16-bit maps (ragged tiles, channel tail, zero-filled borders) against conv2d."""
+    x = rnd(B, C, H, W, seed=1, dtype=dt)
+    w, b = rnd(C, 1, 5, 5, seed=2, scale=0.3, dtype=torch.float32), rnd(C, seed=3, dtype=torch.float32)
+    ref = F.relu(F.conv2d(x.float(), w, b, padding=2, groups=C)).permute(0, 2, 3, 1)
+    ld = (C + 7) // 8 * 8
+    xi = torch.zeros(B, H, W, ld, dtype=dt, device=DEV)
+    xi[..., :C] = x.permute(0, 2, 3, 1)
+    wt = torch.zeros(25, ld, device=DEV)
+    wt[:, :C] = w.reshape(C, 25).t()
+    out = torch.full((B, H, W, ld), 7.0, dtype=dt, device=DEV)
+    call("romab200_dwconv5x5_relu", "rb_dwconv_args", **{"in": xi}, out=out, ldi=ld, ldo=ld, weight=wt, ldw=ld, bias=b, batch=B, h=H, w=W, c=C,
+         dtype=CODE[dt])
+    torch.cuda.synchronize()
+    close(out[..., :C], ref, 6e-2 if dt == torch.bfloat16 else 8e-3)

@@ -13,7 +13,7 @@ from roma_b200.packing import PackedWeights, fold_bn, pad8
 
 def test_library_exports_every_declared_symbol():
     lib = cabi.load_library()
-    assert lib.romab200_abi_version() == 1
+    assert lib.romab200_abi_version() == 2
     assert len(cabi.FUNCTIONS) >= 20
     for fn in cabi.FUNCTIONS:
         assert hasattr(lib, fn), fn
