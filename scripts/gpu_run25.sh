@@ -1,7 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gemm_tc_gpu.py -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/tc.log 2>&1; echo "tc rc=$?"; tail -n 4 gpurun_out/tc.log
-timeout 300 python scripts/gemm_bench.py ref 2>&1 | tail -5
-timeout 900 python -m pytest tests/test_e2e_gpu.py -m gpu -q -s --tb=short -p no:cacheprovider > gpurun_out/e2e.log 2>&1; grep -E "^\[|passed|failed|Error" gpurun_out/e2e.log | tail -n 12
-timeout 600 python bench.py --precision fp16 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_fp16.json 2> gpurun_out/bench_fp16.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_fp16.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['achieved'])"; tail -n 3 gpurun_out/bench_fp16.err
+timeout 900 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:"refiner_prologue_kernel" --launch-count 6 -o gpurun_out/prol -f python scripts/profile_one_pass.py fp16 > gpurun_out/ncu_prol.log 2>&1
+tail -2 gpurun_out/ncu_prol.log
