@@ -484,7 +484,9 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
         }
     }
     // few tiles: keep 128-wide tiles so that more CTAs are in flight
-    if (BN > 128 && ((int64_t)((a->M + 127) / 128) * ((a->N + BN - 1) / BN) * zdim) < 148) BN = 128;
+    // (the threshold is in tiles: below ~100 wide tiles less than 2/3 of the SMs would have work; above it the wider tile wins
+    // because these shapes are bound by L2 -> shared-memory operand traffic, which a 128-wide tile raises by a third)
+    if (BN > 128 && ((int64_t)((a->M + 127) / 128) * ((a->N + BN - 1) / BN) * zdim) < 100) BN = 128;
     CUtensorMap ma, mb;
     if (make_map(&ma, a->A, p.is_bf16, p.ntaps > 1 ? p.k_per_tap : a->K, a_rows, a->lda, p.batch1, a->sa1, batch0, a->sa0, TC_BK, TC_BM)) return 1;
     if (!a->trans_b) {

@@ -201,3 +201,17 @@ def test_dwconv_16bit_tma(dt, B, C, H, W):
          dtype=CODE[dt])
     torch.cuda.synchronize()
     close(out[..., :C], ref, 6e-2 if dt == torch.bfloat16 else 8e-3)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 14, 22), (1, 128, 6, 4), (2, 72, 8, 8)])
+def test_maxpool_16bit_vector(dt, B, C, H, W):
+    """2x2 max-pool between zero-padded channels-last maps, 16-byte vector kernel: exact (a max is a selection)."""
+    x = rnd(B, H, W, C, seed=1, dtype=dt)
+    xin = torch.zeros(B, H + 2, W + 2, C, dtype=dt, device=DEV)
+    xin[:, 1:-1, 1:-1] = x
+    out = torch.zeros(B, H // 2 + 2, W // 2 + 2, C, dtype=dt, device=DEV)
+    call("romab200_maxpool2x2_padded", "rb_maxpool_args", **{"in": xin}, out=out, batch=B, height=H, width=W, channels=C, dtype=CODE[dt])
+    ref = F.max_pool2d(x.permute(0, 3, 1, 2).float(), 2).permute(0, 2, 3, 1)
+    assert torch.equal(out[:, 1:-1, 1:-1].float().cpu(), ref.cpu())
+    assert out[:, 0].abs().max() == 0 and out[:, :, 0].abs().max() == 0 and out[:, -1].abs().max() == 0 and out[:, :, -1].abs().max() == 0

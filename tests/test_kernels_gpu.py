@@ -135,13 +135,19 @@ def test_gemm_coskernel_epilogue():
 
 
 # ----------------------------------------------------------------------------------------------- row-wise
-def test_layernorm():
-    rows, cols = 37, 1024
+@pytest.mark.parametrize("rows,cols,out_dt", [(37, 1024, torch.float32), (3202, 1024, torch.float16), (5, 1024, torch.bfloat16),
+                                              (37, 200, torch.float32), (9, 1000, torch.float16)])
+def test_layernorm(rows, cols, out_dt):
+    """cols == 1024 takes the row-in-registers kernel, everything else the generic warp-per-row one."""
     x, g, b = rnd(rows, cols, seed=1, scale=3.0), rnd(cols, seed=2), rnd(cols, seed=3)
-    y = torch.empty_like(x)
-    call("romab200_layernorm", "rb_layernorm_args", x=x, y=y, gamma=g, beta=b, rows=rows, cols=cols, ldx=cols, ldy=cols,
-         dtype_x=F32, dtype_y=F32, eps=1e-6)
-    close(y, F.layer_norm(x, (cols,), g, b, 1e-6), 2e-5)
+    ldy = (cols + 7) // 8 * 8
+    y = torch.zeros(rows, ldy, dtype=out_dt, device=DEV)
+    code = {torch.float32: F32, torch.float16: cabi.RB_F16, torch.bfloat16: cabi.RB_BF16}[out_dt]
+    call("romab200_layernorm", "rb_layernorm_args", x=x, y=y, gamma=g, beta=b, rows=rows, cols=cols, ldx=cols, ldy=ldy,
+         dtype_x=F32, dtype_y=code, eps=1e-6)
+    ref = F.layer_norm(x, (cols,), g, b, 1e-6)
+    tol = {torch.float32: 2e-5, torch.float16: 1e-2, torch.bfloat16: 8e-2}[out_dt]
+    close(y[:, :cols], ref, tol)
 
 
 def test_copy_split_transpose_tokens_im2col():
