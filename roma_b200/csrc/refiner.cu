@@ -358,90 +358,7 @@ __global__ void __launch_bounds__(256) dwconv5x5_relu_kernel(const T* __restrict
         if (x0 + i < W) ob[(int64_t)(x0 + i) * ldo] = from_f<T>(fmaxf(acc[i], 0.f));
 }
 
-// 16-bit variant: lanes own channel PAIRS (one 32-bit shared-memory word = 2 channels), the tile is staged in the
-// storage dtype with 16-byte global loads, and the 2 x 25 filter taps live in registers.  Per 16x2 outputs a
-// thread issues 100 LDS.32 + 800 FFMA: the kernel is FP32-FMA bound (25 FMA per output element), not LDS bound.
-template <typename T>
-__global__ void __launch_bounds__(128) dwconv5x5_relu_h2_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t ldi, int64_t ldo,
-                                                                const float* __restrict__ wgt, int64_t ldw, const float* __restrict__ bias,
-                                                                int H, int W, int C, int tiles_x) {
-    rb::pdl_wait();
-    // 4 warps, each owns TWO adjacent output rows of the 8x16 tile: the 6 input rows they need are read once
-    // (120 LDS.32 per 64 outputs instead of 200), so the FP32 FMA pipe is the limiter.
-    constexpr int TH = 8, TW = 16, CH = 64, NT = 128;
-    __shared__ __align__(16) T tile[(TH + 4) * (TW + 4) * CH];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-    const int c0 = blockIdx.y * CH, b = blockIdx.z;
-    const int x0 = tx * TW, y0 = ty * TH;
-    const int cpad = (C + 7) & ~7;
-    const T* inb = in + (int64_t)b * H * W * ldi;
-    {   // all global loads of a thread are issued before the first shared store (memory-level parallelism)
-        constexpr int NV = (TH + 4) * (TW + 4) * (CH / 8), PER = (NV + NT - 1) / NT;
-        uint4 vals[PER];
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const int i = threadIdx.x + k * NT;
-            const int pix = i >> 3, v = i & 7;
-            const int py = pix / (TW + 4), px = pix - py * (TW + 4);
-            const int yy = y0 + py - 2, xx = x0 + px - 2;
-            vals[k] = make_uint4(0u, 0u, 0u, 0u);
-            if (i < NV && yy >= 0 && yy < H && xx >= 0 && xx < W && c0 + 8 * v < cpad)
-                vals[k] = *reinterpret_cast<const uint4*>(inb + ((int64_t)yy * W + xx) * ldi + c0 + 8 * v);
-        }
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const int i = threadIdx.x + k * NT;
-            if (i < NV) *reinterpret_cast<uint4*>(&tile[(i >> 3) * CH + 8 * (i & 7)]) = vals[k];
-        }
-    }
-    const int c = c0 + 2 * lane;
-    const bool ok0 = c < C, ok1 = c + 1 < C;
-    float2 wv[25];                                        // (channel c, channel c+1) taps: operands of the packed FFMA2
-#pragma unroll
-    for (int t = 0; t < 25; ++t) wv[t] = make_float2(ok0 ? wgt[(int64_t)t * ldw + c] : 0.f, ok1 ? wgt[(int64_t)t * ldw + c + 1] : 0.f);
-    const float2 bv = make_float2(ok0 ? bias[c] : 0.f, ok1 ? bias[c + 1] : 0.f);
-    __syncthreads();
-    float2 acc[2][TW];
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int i = 0; i < TW; ++i) acc[r][i] = bv;
-#pragma unroll
-    for (int iy = 0; iy < 6; ++iy) {                      // input rows 2*wid + iy of the tile feed output rows 2*wid + {0, 1}
-#pragma unroll
-        for (int px = 0; px < TW + 4; ++px) {
-            T pr[2];
-            *reinterpret_cast<uint32_t*>(pr) = *reinterpret_cast<const uint32_t*>(&tile[((2 * wid + iy) * (TW + 4) + px) * CH + 2 * lane]);
-            const float2 v = make_float2(to_f(pr[0]), to_f(pr[1]));
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int ky = iy - r;
-                if (ky >= 0 && ky < 5) {
-#pragma unroll
-                    for (int kx = 0; kx < 5; ++kx) {
-                        const int ox = px - kx;
-                        if (ox >= 0 && ox < TW) acc[r][ox] = __ffma2_rn(wv[ky * 5 + kx], v, acc[r][ox]);   // 2 fp32 FMAs / instruction (sm_100)
-                    }
-                }
-            }
-        }
-    }
-    if (!ok0) return;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int yy = y0 + 2 * wid + r;
-        if (yy >= H) continue;
-        T* ob = out + ((int64_t)b * H * W + (int64_t)yy * W) * ldo + c;
-#pragma unroll
-        for (int i = 0; i < TW; ++i) {
-            if (x0 + i < W) {
-                T pair[2] = {from_f<T>(fmaxf(acc[r][i].x, 0.f)), from_f<T>(ok1 ? fmaxf(acc[r][i].y, 0.f) : 0.f)};
-                *reinterpret_cast<uint32_t*>(ob + (int64_t)(x0 + i) * ldo) = *reinterpret_cast<uint32_t*>(pair);
-            }
-        }
-    }
-}
+// (the 16-bit maps take the TMA-fed persistent kernel in dwconv_tma.cu)
 
 // --------------------------------------------------------------------------------------------------
 // Fused ConvRefiner block for thin maps (C = 24 at stride 1): depthwise 5x5 + folded BN + ReLU + pointwise

@@ -59,7 +59,7 @@ class Engine:
         self.fused_c144 = True                   # stride-2 refiner blocks as one fused DW + tcgen05-PW kernel
         self._side = None
         self.profile: Optional[dict] = None      # set to {} to collect CUDA-event timings per stage (bench.py)
-        self.gemm_profile: Optional[list] = None  # set to [] to time every GEMM launch: (backend, flops, start, end)
+        self.gemm_profile: Optional[list] = None  # set to [] to time every GEMM launch: (backend, flops, start, end, shape, epilogue)
 
     @contextmanager
     def stage(self, name):
@@ -143,7 +143,7 @@ class Engine:
         end.record()
         flops = 2.0 * M * N * K * args["batch0"] * args["batch1"]
         self.gemm_profile.append(("simt" if args["dtype_ab"] == cabi.RB_F32 else "tcgen05", flops, start, end,
-                                  (M, N, K, args["batch0"] * args["batch1"])))
+                                  (M, N, K, args["batch0"] * args["batch1"]), args.get("epi", cabi.EPI_LINEAR)))
 
     def layernorm(self, x, y, gb, rows, cols, eps, dtype_y=None):
         call("romab200_layernorm", "rb_layernorm_args", x=x, y=y, gamma=gb[0], beta=gb[1], rows=rows, cols=cols,

@@ -9,9 +9,19 @@ want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
-        "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum"]
+        "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum", "sm__cycles_active.avg"]
+unique = "--unique" in sys.argv
 idx = [(h, hdr.index(h)) for h in want if h in hdr]
+seen = set()
 for r in rows[2:]:
+    key = (r[hdr.index("Kernel Name")], r[hdr.index("Grid Size")])
+    if unique and key in seen:
+        continue
+    seen.add(key)
     print("-" * 100)
     for h, i in idx:
         print(f"{h:70s} {r[i]} {units[i]}")
