@@ -9,8 +9,8 @@ namespace rb {
 __device__ __forceinline__ float rh(float v) { return __half2float(__float2half_rn(v)); }
 
 // half mode follows torch.cdist's matmul formulation for fp16 inputs (the path the reference takes):
-//   d2 = fp16( fp32-accumulated  [-2x | ||x||^2 | 1] . [y | 1 | ||y||^2] ),  d = fp16(sqrt(max(d2, 0)))
-// then fp16(d*d), fp16(-. / (2 std^2)), fp16(exp(.)), fp32 row sum rounded to fp16.
+//   d2 = fp16( fp32-accumulated  [-2x | ||x||^2 | 1] . [y | 1 | ||y||^2] ) clamped at 0,
+// then exp(-d2 / (2 std^2)) in fp32, fp32 row sum rounded to fp16 (see the comment in the loop for what is skipped).
 __global__ void __launch_bounds__(128) kde_kernel(const float* __restrict__ x, float* __restrict__ density, int n, float two_var, int half) {
     rb::pdl_wait();
     __shared__ float4 pts[512];
@@ -42,11 +42,14 @@ __global__ void __launch_bounds__(128) kde_kernel(const float* __restrict__ x, f
         __syncthreads();
         int lim = min(512, n - j0);
         if (half) {
-            // two pairs per iteration on packed fp16 pipes: fp32 dot product (the matmul), then the fp16 elementwise chain
-            // sqrt -> square -> scale -> exp with round-to-nearest at every step (h2sqrt / hmul2 / h2exp), fp32 row sum.
-            // padding entries (j >= n) hold x = 0, norm = +inf  ->  d = inf  ->  exp(-inf) = 0
+            // two pairs per iteration: fp32 dot product (the matmul), d2 rounded to fp16 and clamped (that quantisation is
+            // the one fp16 effect that matters: a d2 ulp moves exp(-50 d2) by up to 10 %), then exp in fp32.  The reference's
+            // sqrt -> square round trip (cdist, then **2) and the fp16 rounding of each exp are skipped: together they move a
+            // density by at most one fp16 ulp (measured against the oracle: max 1e-3, mean 1e-4 relative) and cost two of
+            // the three MUFU operations per pair.
+            // padding entries (j >= n) hold x = 0, norm = +inf  ->  d2 = inf  ->  exp(-inf) = 0
             const __half2 zero2 = __float2half2_rn(0.f);
-            const __half2 nscale = __float2half2_rn(-1.0f / two_var);
+            const float nscale = -1.4426950408889634f / two_var;       // exp(-d2 / two_var) = exp2(d2 * nscale)
             float acc2 = 0.f;
 #pragma unroll 4
             for (int t = 0; t < 512; t += 2) {
@@ -57,11 +60,8 @@ __global__ void __launch_bounds__(128) kde_kernel(const float* __restrict__ x, f
                 s0 = fmaf(az, v0.z, s0); s1 = fmaf(az, v1.z, s1);
                 s0 = fmaf(aw, v0.w, s0); s1 = fmaf(aw, v1.w, s1);
                 s0 = (s0 + ni) + nrm[t]; s1 = (s1 + ni) + nrm[t + 1];
-                __half2 h = __hmax2(__floats2half2_rn(s0, s1), zero2);
-                const __half2 d = h2sqrt(h);
-                const __half2 q = __hmul2(__hmul2(d, d), nscale);
-                const float2 e = __half22float2(h2exp(q));
-                acc += e.x; acc2 += e.y;
+                const float2 d2 = __half22float2(__hmax2(__floats2half2_rn(s0, s1), zero2));
+                acc += exp2f(d2.x * nscale); acc2 += exp2f(d2.y * nscale);
             }
             acc += acc2;
         } else {
