@@ -141,9 +141,23 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keeps stdout to the single JSON line
+        # stdout must carry the single JSON line only: NCCL prints its version banner to stdout when NCCL_DEBUG=VERSION comes
+        # from the environment or from an nccl.conf (seen on the GPU boxes), so the level is pinned unless the caller asked for
+        # more, and communicator creation (init + first collective) runs with fd 1 pointed at stderr
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     amp = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.precision]
     mw, dw = synthetic.make_weights(0)
     model = roma_outdoor(dev, weights=mw, dinov2_weights=dw, coarse_res=COARSE, upsample_res=UPSAMPLE, amp_dtype=amp)
