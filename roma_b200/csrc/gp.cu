@@ -2,14 +2,18 @@
 // and the two triangular solves with the Fourier basis as right-hand sides, without leaving the GPU
 // and without cuSOLVER.
 //
-// Blocked right-looking factorisation with 32-wide panels on an augmented workspace
+// Blocked right-looking factorisation on an augmented workspace
 //      W = [ K_yy + sigma I ]   n rows
 //          [      F^T       ]   nrhs rows
 // Applying the panel solve and trailing update to the F^T rows as well turns them into (L^-1 F)^T, so the
 // forward substitution is free.  The backward substitution then runs row-wise on those rows
-// (X^T L = Y^T), again panel by panel, and leaves alpha^T = X^T in place: exactly the [N,K] operand
-// layout that mu = K_xy @ alpha needs.  Panel kernels are latency-bound (one thread per row, 32-step
-// recurrences held in registers); all O(n^3) work is in the trailing updates, which are romab200 GEMMs.
+// (X^T L = Y^T), again block by block, and leaves alpha^T = X^T in place: exactly the [N,K] operand
+// layout that mu = K_xy @ alpha needs.  Three schedules of the same algorithm (rb_gp_solve_args.algo):
+//   2 (the engine's default)  128-wide blocks: chol_block128_kernel factors the diagonal block in shared memory and
+//                             forms its inverse, every other step is a K = 128 GEMM (13 dependent steps for n = 1600)
+//   0                         32-wide panels as a chain of small kernels (chol_diag / chol_panel / trsm_back + GEMMs)
+//   1                         one cooperative persistent kernel with device-wide barriers
+// All O(n^3) work is in the trailing updates, which are romab200 fp32 GEMMs (lower triangle only).
 #include "common.cuh"
 
 namespace rb {
