@@ -145,6 +145,8 @@ int romab200_assemble_tokens(const rb_tokens_args* args, void* stream);
  * W is a batch of workspaces [n + nrhs, n] (row-major, pitch ldw): rows 0..n-1 hold the SPD matrix
  * K_yy + sigma*I (lower triangle is read), rows n.. hold F^T ([nrhs, n]).  On return rows n.. hold
  * X^T where (K_yy + sigma I) X = F, i.e. alpha^T, ready to be the [N,K] operand of mu = K_xy @ alpha.
+ * With algo 0 and 2 the lower triangle of rows 0..n-1 holds the Cholesky factor afterwards; the strict upper triangle is
+ * unspecified (symmetric trailing updates only maintain the lower half).
  * Replaces torch.linalg.cholesky + torch.cholesky_solve (matcher.py:307-308). */
 typedef struct {
     float* W; int32_t n, nrhs, batch; int64_t ldw, stride;
