@@ -13,6 +13,11 @@
  *   - activations are channels-last ("NHWC"): a [B,H,W,C] map is a row-major [B*H*W, C] matrix with an
  *     explicit row pitch, so 1x1 convolutions and Linear layers are the same GEMM;
  *   - dtypes: RB_F32 / RB_F16 / RB_BF16; accumulation is always fp32.
+ *   - RB_F16S ("split fp16 pair") is the storage format of the tensor-core parity mode: a matrix is held as TWO fp16
+ *     planes of the same pitch, hi = fp16(x) and lo = fp16((x - hi) * 2^11), value = hi + lo * 2^-11: 22 significand bits
+ *     with the exponent range of fp16 (the reference's own CUDA autocast range).  romab200_gemm contracts such operands
+ *     with three tcgen05 MMAs per k-step (hi.hi + 2^-11 (hi.lo + lo.hi), fp32 accumulation in TMEM), which reproduces an
+ *     fp32 GEMM to ~2^-22 relative; arguments named *_lo carry the second plane.
  */
 #ifndef ROMAB200_H
 #define ROMAB200_H
@@ -23,9 +28,9 @@
 extern "C" {
 #endif
 
-#define ROMAB200_ABI_VERSION 2
+#define ROMAB200_ABI_VERSION 3
 
-enum rb_dtype { RB_F32 = 0, RB_F16 = 1, RB_BF16 = 2 };
+enum rb_dtype { RB_F32 = 0, RB_F16 = 1, RB_BF16 = 2, RB_F16S = 3 };
 enum rb_act { RB_ACT_NONE = 0, RB_ACT_RELU = 1, RB_ACT_GELU = 2 };
 enum rb_rowmap { RB_ROWMAP_NONE = 0, RB_ROWMAP_PAD_KEEP = 1, RB_ROWMAP_PAD_TO_COMPACT = 2, RB_ROWMAP_SEGMENT = 3 };
 enum rb_epi { RB_EPI_LINEAR = 0, RB_EPI_COSKERNEL = 1 };
@@ -80,6 +85,9 @@ typedef struct {
     float eps, inv_t, diag_add; int32_t cos_normalized;
     int32_t rowmap, pad_h, pad_w, seg_in, seg_out, seg_off;
     int32_t backend;
+    /* second planes of RB_F16S operands / output (dtype_ab == RB_F16S: A_lo and B_lo, same geometry as A and B;
+       dtype_c == RB_F16S: C_lo, same pitch as C); NULL otherwise */
+    const void* A_lo; const void* B_lo; void* C_lo;
 } rb_gemm_args;
 int romab200_gemm(const rb_gemm_args* args, void* stream);
 
@@ -87,11 +95,14 @@ int romab200_gemm(const rb_gemm_args* args, void* stream);
 typedef struct {
     const void* x; void* y; const float* gamma; const float* beta;
     int64_t rows; int32_t cols; int64_t ldx, ldy; int32_t dtype_x, dtype_y; float eps;
+    void* y_lo;   /* second plane when dtype_y == RB_F16S */
 } rb_layernorm_args;
 int romab200_layernorm(const rb_layernorm_args* args, void* stream);
 
-/* In-place row softmax of attention scores: s = softmax(scale * s) over `cols` (SDPA, attention.py:59) */
-typedef struct { void* s; int64_t rows; int32_t cols; int64_t lds; int32_t dtype; float scale; } rb_softmax_args;
+/* Row softmax of attention scores: s = softmax(scale * s) over `cols` (SDPA, attention.py:59); in place, or (out_hi != NULL,
+ * dtype RB_F32) written as an RB_F16S pair of planes [rows, ldo] for the split-fp16 PV product (pad columns receive 0) */
+typedef struct { void* s; int64_t rows; int32_t cols; int64_t lds; int32_t dtype; float scale;
+                 void* out_hi; void* out_lo; int64_t ldo; } rb_softmax_args;
 int romab200_softmax_rows(const rb_softmax_args* args, void* stream);
 
 /* Fused attention forward (F.scaled_dot_product_attention, attention.py:50-63), 16-bit tensor-core path:
@@ -122,15 +133,24 @@ typedef struct {
 } rb_split_args;
 int romab200_split_f16x3(const rb_split_args* args, void* stream);
 
+/* fp32 matrix -> RB_F16S planes: hi[r,c] = fp16(v), lo[r,c] = fp16((v - hi) * 2^11), v = x[r,c] (/ row_norm[r] if given).
+ * The producer of every split-fp16 GEMM operand that is not written in that format by its own kernel. */
+typedef struct {
+    const float* x; void* hi; void* lo; int64_t rows; int32_t cols; int64_t ldx, ldd; const float* row_norm;
+} rb_split_pair_args;
+int romab200_split_f16s(const rb_split_pair_args* args, void* stream);
+
 /* ---- VGG19-BN pieces that are not GEMMs (encoders.py:17-27) ------------------------------------ */
 /* First conv (3 -> 64) + folded BN + ReLU, NCHW fp32 image -> zero-padded NHWC [B,H+2,W+2,64] */
 typedef struct {
     const float* image; void* out; const float* weight /* [64][27] folded */; const float* bias /* [64] */;
     int32_t batch, height, width, cout; int32_t dtype_out;
+    void* out_lo;   /* second plane when dtype_out == RB_F16S */
 } rb_conv_first_args;
 int romab200_conv3x3_first(const rb_conv_first_args* args, void* stream);
 /* 2x2/2 max-pool between zero-padded NHWC maps: [B,H+2,W+2,C] -> [B,H/2+2,W/2+2,C] */
-typedef struct { const void* in; void* out; int32_t batch, height, width, channels, dtype; } rb_maxpool_args;
+typedef struct { const void* in; void* out; int32_t batch, height, width, channels, dtype;
+                 const void* in_lo; void* out_lo; /* second planes when dtype == RB_F16S */ } rb_maxpool_args;
 int romab200_maxpool2x2_padded(const rb_maxpool_args* args, void* stream);
 
 /* ---- DINOv2 tokenisation (dinov2.py:192-201, patch_embed.py:69-82) ------------------------------ */
@@ -196,6 +216,8 @@ int romab200_local_corr(const rb_local_corr_args* args, void* stream);
 typedef struct {
     const void* in; void* out; int64_t ldi, ldo; const float* weight; int64_t ldw; const float* bias;
     int32_t batch, h, w, c; int32_t dtype;
+    void* out_lo;   /* dtype == RB_F32 only: when non-NULL the result is written as an RB_F16S pair (out = hi plane, out_lo =
+                       lo plane, pitch ldo in fp16 elements) so that the pointwise GEMM can consume it directly */
 } rb_dwconv_args;
 int romab200_dwconv5x5_relu(const rb_dwconv_args* args, void* stream);
 

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "romab200.h")
 LIB_PATH = os.path.join(HERE, "lib", "libromab200.so")
 
-RB_F32, RB_F16, RB_BF16 = 0, 1, 2
+RB_F32, RB_F16, RB_BF16, RB_F16S = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 ROWMAP_NONE, ROWMAP_PAD_KEEP, ROWMAP_PAD_TO_COMPACT, ROWMAP_SEGMENT = 0, 1, 2, 3
 EPI_LINEAR, EPI_COSKERNEL = 0, 1

@@ -47,7 +47,29 @@ __device__ __forceinline__ void store_any(void* p, int64_t i, int dtype, float v
     else ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
 }
 
+// bytes per element of one plane (RB_F16S = two fp16 planes of the same pitch)
 __host__ __device__ __forceinline__ int dtype_size(int dtype) { return dtype == RB_F32 ? 4 : 2; }
+
+// ---- split-fp16 pair: x ~ hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11) -------------------------------
+// 22 significand bits, the exponent range of fp16, and no underflow of the low part (it is stored at the magnitude of x).
+// Re-splitting a reconstructed value is exact, so kernels may pass maps through unchanged (max-pool, copies).
+constexpr float RB_SPLIT_SCALE = 2048.0f;
+__device__ __forceinline__ void split_f16s(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * RB_SPLIT_SCALE);
+}
+__device__ __forceinline__ float join_f16s(__half hi, __half lo) { return fmaf(__half2float(lo), 1.0f / RB_SPLIT_SCALE, __half2float(hi)); }
+// stores `v` as `dtype` at element i of p (and of p_lo for RB_F16S)
+__device__ __forceinline__ void store_split_any(void* p, void* p_lo, int64_t i, int dtype, float v) {
+    if (dtype == RB_F16S) {
+        __half hi, lo;
+        split_f16s(v, hi, lo);
+        ((__half*)p)[i] = hi; ((__half*)p_lo)[i] = lo;
+    } else {
+        store_any(p, i, dtype, v);
+    }
+}
+inline int current_device() { int d = 0; cudaGetDevice(&d); return d; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -67,7 +89,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // GEMM epilogue shared by the SIMT and tcgen05 back-ends
 // ------------------------------------------------------------------------------------------------
 struct Epilogue {
-    void* C; int64_t ldc; int dtype_c;
+    void* C; void* C_lo; int64_t ldc; int dtype_c;
     float alpha;
     const float* bias; const float* col_scale;
     const void* R; int64_t ldr; int dtype_r;
@@ -109,7 +131,7 @@ struct Epilogue {
         if (m >= M || n >= N) return;
         int64_t orow = map_row(m);
         if (orow < 0) return;
-        store_any(C, orow * ldc + n, dtype_c, apply(acc, m, n, orow));
+        store_split_any(C, C_lo, orow * ldc + n, dtype_c, apply(acc, m, n, orow));
     }
 };
 

@@ -26,12 +26,30 @@ __global__ void layernorm_kernel(const TI* __restrict__ x, TO* __restrict__ y, c
     for (int c = lane; c < cols; c += 32) yr[c] = from_f<TO>((to_f(xr[c]) - mean) * rstd * g[c] + b[c]);
 }
 
+// the same with an RB_F16S (split fp16 pair) result
+__global__ void layernorm_split_kernel(const float* __restrict__ x, __half* __restrict__ yh, __half* __restrict__ yl, const float* __restrict__ g,
+                                       const float* __restrict__ b, int64_t rows, int cols, int64_t ldx, int64_t ldy, float eps) {
+    rb::pdl_wait();
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (row >= rows) return;
+    int lane = threadIdx.x & 31;
+    const float* xr = x + row * ldx;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += xr[c];
+    float mean = warp_sum(s) / cols;
+    float v = 0.f;
+    for (int c = lane; c < cols; c += 32) { float d = xr[c] - mean; v += d * d; }
+    float rstd = rsqrtf(warp_sum(v) / cols + eps);
+    for (int c = lane; c < cols; c += 32) split_f16s((xr[c] - mean) * rstd * g[c] + b[c], yh[row * ldy + c], yl[row * ldy + c]);
+}
+
 // Row-in-registers variant for fp32 rows of NV * 128 columns (the ViT and decoder width 1024: NV = 8): the row is read
 // once with 16-byte loads (the generic kernel reads it three times with 4-byte loads and ran at a third of the HBM
 // rate), mean and centred variance are formed from the registers, the result is written with 8/16-byte stores.
-template <typename TO, int NV>
+template <typename TO, int NV, bool SPLIT = false>
 __global__ void __launch_bounds__(128) layernorm_vec_kernel(const float* __restrict__ x, TO* __restrict__ y, const float* __restrict__ g,
-                                                            const float* __restrict__ b, int64_t rows, int64_t ldx, int64_t ldy, float eps) {
+                                                            const float* __restrict__ b, int64_t rows, int64_t ldx, int64_t ldy, float eps,
+                                                            TO* __restrict__ y_lo = nullptr) {
     rb::pdl_wait();
     const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -58,7 +76,12 @@ __global__ void __launch_bounds__(128) layernorm_vec_kernel(const float* __restr
         const int c = (k * 32 + lane) * 4;
         const float4 gg = *reinterpret_cast<const float4*>(g + c), bb = *reinterpret_cast<const float4*>(b + c);
         const float o0 = v[k].x * rstd * gg.x + bb.x, o1 = v[k].y * rstd * gg.y + bb.y, o2 = v[k].z * rstd * gg.z + bb.z, o3 = v[k].w * rstd * gg.w + bb.w;
-        if constexpr (sizeof(TO) == 4) {
+        if constexpr (SPLIT) {
+            __half hi[4], lo[4];
+            split_f16s(o0, hi[0], lo[0]); split_f16s(o1, hi[1], lo[1]); split_f16s(o2, hi[2], lo[2]); split_f16s(o3, hi[3], lo[3]);
+            *reinterpret_cast<uint2*>(yr + c) = *reinterpret_cast<uint2*>(hi);
+            *reinterpret_cast<uint2*>(y_lo + row * ldy + c) = *reinterpret_cast<uint2*>(lo);
+        } else if constexpr (sizeof(TO) == 4) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(yr) + c) = make_float4(o0, o1, o2, o3);
         } else {
             TO pk[4] = {from_f<TO>(o0), from_f<TO>(o1), from_f<TO>(o2), from_f<TO>(o3)};
@@ -147,6 +170,53 @@ __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(T* __restrict__ 
     }
 }
 
+// fp32 scores -> softmax written as an RB_F16S pair (the A operand of the split-fp16 PV product); not in place
+__global__ void __launch_bounds__(256) softmax_rows_split_kernel(const float* __restrict__ s, __half* __restrict__ oh, __half* __restrict__ ol,
+                                                                 int64_t rows, int cols, int64_t lds, int64_t ldo, float scale) {
+    rb::pdl_wait();
+    constexpr int VN = 4, ITERS = 2048 / (32 * VN);
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* sr = s + row * lds;
+    float v[ITERS][VN];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+        const int c0 = (i * 32 + lane) * VN;
+        if (c0 < cols) {
+            const float4 raw = *reinterpret_cast<const float4*>(sr + c0);
+            const float e[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int j = 0; j < VN; ++j) {
+                v[i][j] = (c0 + j < cols) ? e[j] * scale : -INFINITY;
+                m = fmaxf(m, v[i][j]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < VN; ++j) v[i][j] = -INFINITY;
+        }
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i)
+#pragma unroll
+        for (int j = 0; j < VN; ++j) { v[i][j] = expf(v[i][j] - m); sum += v[i][j]; }
+    const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+        const int c0 = (i * 32 + lane) * VN;
+        if (c0 < cols) {
+            __half hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < VN; ++j) split_f16s(v[i][j] * inv, hi[j], lo[j]);          // pad columns (>= cols) receive 0
+            *reinterpret_cast<uint2*>(oh + row * ldo + c0) = *reinterpret_cast<uint2*>(hi);
+            *reinterpret_cast<uint2*>(ol + row * ldo + c0) = *reinterpret_cast<uint2*>(lo);
+        }
+    }
+}
+
 template <typename T>
 __global__ void row_norms_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t rows, int cols, int64_t ldx) {
     rb::pdl_wait();
@@ -189,6 +259,35 @@ __global__ void split_f16x3_kernel(const float* __restrict__ x, __half* __restri
         d[c] = hi;
         d[cols + c] = layout_b ? hi : lo;
         d[2 * cols + c] = layout_b ? lo : hi;
+    }
+}
+
+// fp32 -> RB_F16S planes, 4 elements per thread (16-byte load, two 8-byte stores); pitches are multiples of 4 elements
+__global__ void __launch_bounds__(256) split_f16s_vec_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                             int64_t rows, int cols4, int cols, int64_t ldx, int64_t ldd,
+                                                             const float* __restrict__ norm) {
+    rb::pdl_wait();
+    const int64_t total = rows * cols4;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / cols4; const int c = (int)(idx - r * cols4) * 4;
+        float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+        if (norm) { const float n = norm[r]; v.x /= n; v.y /= n; v.z /= n; v.w /= n; }
+        // the pitch pads beyond `cols` (at most 3 elements here) are written too: the GEMM never reads past K (TMA zero fill)
+        __half h[4], l[4];
+        split_f16s(v.x, h[0], l[0]); split_f16s(v.y, h[1], l[1]); split_f16s(v.z, h[2], l[2]); split_f16s(v.w, h[3], l[3]);
+        *reinterpret_cast<uint2*>(hi + r * ldd + c) = *reinterpret_cast<uint2*>(h);
+        *reinterpret_cast<uint2*>(lo + r * ldd + c) = *reinterpret_cast<uint2*>(l);
+    }
+}
+__global__ void split_f16s_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t rows, int cols,
+                                  int64_t ldx, int64_t ldd, const float* __restrict__ norm) {
+    rb::pdl_wait();
+    const int64_t total = rows * cols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / cols; const int c = (int)(idx - r * cols);
+        float v = x[r * ldx + c];
+        if (norm) v = v / norm[r];
+        split_f16s(v, hi[r * ldd + c], lo[r * ldd + c]);
     }
 }
 
@@ -256,10 +355,22 @@ extern "C" int romab200_layernorm(const rb_layernorm_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->rows > 0 && a->cols > 0, "layernorm: empty input");
     const int esy = a->dtype_y == RB_F32 ? 4 : 2;
+    RB_REQUIRE(a->dtype_y != RB_F16S || (a->y_lo && a->dtype_x == RB_F32), "layernorm: RB_F16S output needs y_lo and fp32 input");
+    if (a->dtype_y == RB_F16S && !(a->cols == 1024 && a->ldx % 4 == 0 && a->ldy % 4 == 0 && ((uintptr_t)a->x) % 16 == 0 &&
+                                   ((uintptr_t)a->y) % 8 == 0 && ((uintptr_t)a->y_lo) % 8 == 0 && ((uintptr_t)a->gamma) % 16 == 0 && ((uintptr_t)a->beta) % 16 == 0)) {
+        dim3 grid((unsigned)((a->rows + 7) / 8));
+        rb::launch_pdl(layernorm_split_kernel, grid, dim3(256), 0, st, (const float*)a->x, (__half*)a->y, (__half*)a->y_lo, a->gamma, a->beta, a->rows, a->cols, a->ldx, a->ldy, a->eps);
+        return check_launch("layernorm");
+    }
+    if (a->dtype_y == RB_F16S) {
+        dim3 gridv((unsigned)((a->rows + 3) / 4));
+        rb::launch_pdl(layernorm_vec_kernel<__half, 8, true>, gridv, dim3(128), 0, st, (const float*)a->x, (__half*)a->y, a->gamma, a->beta, a->rows, a->ldx, a->ldy, a->eps, (__half*)a->y_lo);
+        return check_launch("layernorm");
+    }
     if (a->dtype_x == RB_F32 && a->cols == 1024 && a->ldx % 4 == 0 && (a->ldy * esy) % 16 == 0 && ((uintptr_t)a->x) % 16 == 0 &&
         ((uintptr_t)a->y) % 16 == 0 && ((uintptr_t)a->gamma) % 16 == 0 && ((uintptr_t)a->beta) % 16 == 0) {
         dim3 gridv((unsigned)((a->rows + 3) / 4));
-#define LNV(TO) rb::launch_pdl(layernorm_vec_kernel<TO, 8>, gridv, dim3(128), 0, st, (const float*)a->x, (TO*)a->y, a->gamma, a->beta, a->rows, a->ldx, a->ldy, a->eps)
+#define LNV(TO) rb::launch_pdl(layernorm_vec_kernel<TO, 8, false>, gridv, dim3(128), 0, st, (const float*)a->x, (TO*)a->y, a->gamma, a->beta, a->rows, a->ldx, a->ldy, a->eps, (TO*)nullptr)
         if (a->dtype_y == RB_F32) LNV(float); else if (a->dtype_y == RB_F16) LNV(__half); else LNV(__nv_bfloat16);
 #undef LNV
         return check_launch("layernorm");
@@ -280,6 +391,14 @@ extern "C" int romab200_softmax_rows(const rb_softmax_args* a, void* stream) {
     RB_REQUIRE(a->rows > 0 && a->cols > 0 && a->rows < (1ll << 31), "softmax: bad shape");
     const int es = a->dtype == RB_F32 ? 4 : 2;
     const int vn = 16 / es;
+    if (a->out_hi) {
+        RB_REQUIRE(a->dtype == RB_F32 && a->out_lo && a->cols <= 2048 && a->lds % 4 == 0 && a->ldo % 4 == 0 && (a->cols + 3) / 4 * 4 <= a->ldo &&
+                   (a->cols + 3) / 4 * 4 <= a->lds && ((uintptr_t)a->s) % 16 == 0 && ((uintptr_t)a->out_hi) % 8 == 0 && ((uintptr_t)a->out_lo) % 8 == 0,
+                   "softmax: split output needs fp32 scores, <= 2048 columns and 4-element aligned pitches");
+        rb::launch_pdl(softmax_rows_split_kernel, dim3((unsigned)((a->rows + 7) / 8)), dim3(256), 0, st, (const float*)a->s, (__half*)a->out_hi, (__half*)a->out_lo,
+                       a->rows, a->cols, a->lds, a->ldo, a->scale);
+        return check_launch("softmax_rows");
+    }
     // rows must be padded to whole 16-byte vectors (the pad columns are rewritten with zeros)
     if (a->cols <= 2048 && (a->lds * es) % 16 == 0 && ((uintptr_t)a->s) % 16 == 0 && (a->cols + vn - 1) / vn * vn <= a->lds) {
         unsigned grid = (unsigned)((a->rows + 7) / 8);
@@ -318,6 +437,21 @@ extern "C" int romab200_split_f16x3(const rb_split_args* a, void* stream) {
     rb::launch_pdl(split_f16x3_kernel, dim3(grid_for(a->rows * a->cols, 256)), dim3(256), 0, st, a->x, (__half*)a->dst, a->rows, a->cols, a->ldx, a->ldd,
                                                                         a->row_norm, a->layout_b);
     return check_launch("split_f16x3");
+}
+
+extern "C" int romab200_split_f16s(const rb_split_pair_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->x && a->hi && a->lo && a->rows > 0 && a->cols > 0 && a->ldd >= a->cols, "split_f16s: bad arguments");
+    const int cols4 = (a->cols + 3) / 4;
+    if (a->ldx % 4 == 0 && a->ldd % 4 == 0 && (int64_t)cols4 * 4 <= a->ldx && (int64_t)cols4 * 4 <= a->ldd && ((uintptr_t)a->x) % 16 == 0 &&
+        ((uintptr_t)a->hi) % 8 == 0 && ((uintptr_t)a->lo) % 8 == 0) {
+        rb::launch_pdl(split_f16s_vec_kernel, dim3(grid_for(a->rows * cols4, 256)), dim3(256), 0, st, a->x, (__half*)a->hi, (__half*)a->lo, a->rows, cols4,
+                       a->cols, a->ldx, a->ldd, a->row_norm);
+    } else {
+        rb::launch_pdl(split_f16s_kernel, dim3(grid_for(a->rows * a->cols, 256)), dim3(256), 0, st, a->x, (__half*)a->hi, (__half*)a->lo, a->rows, a->cols,
+                       a->ldx, a->ldd, a->row_norm);
+    }
+    return check_launch("split_f16s");
 }
 
 extern "C" int romab200_im2col_patch(const rb_im2col_args* a, void* stream) {

@@ -12,7 +12,7 @@ namespace rb {
 
 Epilogue make_epilogue(const rb_gemm_args* a) {
     Epilogue e;
-    e.C = a->C; e.ldc = a->ldc; e.dtype_c = a->dtype_c;
+    e.C = a->C; e.C_lo = a->C_lo; e.ldc = a->ldc; e.dtype_c = a->dtype_c;
     e.alpha = a->alpha;
     e.bias = a->bias; e.col_scale = a->col_scale;
     e.R = a->R; e.ldr = a->ldr; e.dtype_r = a->dtype_r;
@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
     // epilogue
     Epilogue e = p.epi;
     e.C = (char*)e.C + (z0 * p.sc0 + z1 * p.sc1) * dtype_size(e.dtype_c);
+    if (e.C_lo) e.C_lo = (char*)e.C_lo + (z0 * p.sc0 + z1 * p.sc1) * 2;
     if (e.R) e.R = (const char*)e.R + (z0 * p.sr0 + z1 * p.sr1) * dtype_size(e.dtype_r);
     if (e.norm_a) e.norm_a += z0 * p.sna0;
     if (e.norm_b) e.norm_b += z0 * p.snb0;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (n + j < p.N) store_any(e.C, orow * e.ldc + n + j, e.dtype_c, e.apply(acc[i][jg + j], m, n + j, orow));
+                    if (n + j < p.N) store_split_any(e.C, e.C_lo, orow * e.ldc + n + j, e.dtype_c, e.apply(acc[i][jg + j], m, n + j, orow));
             }
         }
     }

@@ -11,6 +11,13 @@
 // just a per-k-block row offset on the TMA coordinate; out-of-range rows/columns are zero-filled by TMA,
 // which also handles M/N/K tails, so no operand is ever padded or copied.
 // Batched GEMMs (attention heads) use the 3rd/4th tensor-map dimension.
+//
+// SPLIT variant (dtype_ab == RB_F16S): fp32-class accuracy on the f16 tensor pipe.  Every operand element x is stored
+// as two fp16 planes, hi = fp16(x) and lo = fp16((x - hi) * 2^11), i.e. 22 significand bits with the exponent range of
+// fp16 and no underflow of the low part.  Per k-step the MMA thread issues three instructions into two TMEM
+// accumulators, acc0 += A_hi.B_hi and acc1 += A_hi.B_lo + A_lo.B_hi; the epilogue forms acc0 + acc1 * 2^-11 (the
+// dropped A_lo.B_lo term is 2^-22 relative).  Products of fp16 values are exact in the fp32 accumulator, so the only
+// error left is the 2^-22 operand representation and the fp32 accumulation itself.
 #include "common.cuh"
 #include <cuda.h>
 
@@ -122,18 +129,26 @@ struct TcParams {
 
 constexpr int TC_BM = 128, TC_BK = 64;
 
-template <int BN> struct TcCfg {
+template <int BN, bool SPLIT> struct TcCfg {
     // BN = 256: one CTA per SM with 8 epilogue warps; narrower tiles: two CTAs per SM (two MMA-issuing threads keep the
-    // tensor pipe fed when a k-block is only 128-256 MMA cycles) with 4 epilogue warps each
-    static constexpr int STAGES = BN >= 256 ? 4 : (BN > 128 ? 5 : (BN >= 128 ? 3 : 4));
-    static constexpr int CTAS_PER_SM = BN > 128 ? 1 : 2;
-    static constexpr int EPI_WARPS = BN > 128 ? 8 : 4;
-    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    // tensor pipe fed when a k-block is only 128-256 MMA cycles) with 4 epilogue warps each.  The split variant always
+    // runs one CTA per SM (its two accumulators take up to all 512 TMEM columns).
+    static constexpr int NOPS = SPLIT ? 2 : 1;                           // operand planes per matrix
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;
     static constexpr int B_BYTES = BN * TC_BK * 2;
+    static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = SPLIT ? (BN > 144 ? 2 : (BN > 64 ? 3 : 4))
+                                        : (BN >= 256 ? 4 : (BN > 128 ? 5 : (BN >= 128 ? 3 : 4)));
+    static constexpr int CTAS_PER_SM = (SPLIT || BN > 128) ? 1 : 2;
+    static constexpr int EPI_WARPS = BN > 128 ? 8 : 4;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
     static constexpr int EPI_BYTES = 2 * 256 * 4;                        // staged bias / column-scale (or norm_b) of the tile
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
-    static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));   // two accumulator stages
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
+    static constexpr int ACC_COLS = NOPS * BN;                           // TMEM columns of one accumulator stage
+    static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;       // double-buffered when it fits
+    static constexpr int ACC_TOTAL = ACC_STAGES * ACC_COLS;
+    static constexpr int TMEM_COLS = ACC_TOTAL <= 32 ? 32 : (ACC_TOTAL <= 64 ? 64 : (ACC_TOTAL <= 128 ? 128 : (ACC_TOTAL <= 256 ? 256 : 512)));
+    static_assert(SMEM <= 232448, "shared memory budget");
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -141,24 +156,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 // Persistent kernel: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (m fastest, so CTAs that run
-// together share the same weight tile in L2).  The accumulator is double-buffered in TMEM: the MMA warp starts the
-// next tile while the epilogue warps drain the previous one.
-template <int BN>
-__global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                                                         const TcParams p) {
-    using Cfg = TcCfg<BN>;
+// together share the same weight tile in L2).  The accumulator is double-buffered in TMEM when it fits: the MMA warp
+// starts the next tile while the epilogue warps drain the previous one.
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(TcCfg<BN, SPLIT>::THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
+    using Cfg = TcCfg<BN, SPLIT>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
+    constexpr int OFF_A_LO = A_BYTES, OFF_B = Cfg::NOPS * A_BYTES, OFF_B_LO = Cfg::NOPS * A_BYTES + B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;       // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-    float* s_vec0 = reinterpret_cast<float*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES) + 256);   // bias      | norm_b
-    float* s_vec1 = s_vec0 + 256;                                                                     // col_scale
+    float* s_vec0 = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);   // bias      | norm_b
+    float* s_vec1 = s_vec0 + 256;                                                        // col_scale
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = (p.K + TC_BK - 1) / TC_BK;
@@ -191,17 +207,22 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
-                    mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
+                    mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
                     int tap = 0, kin = kb * TC_BK, shift = 0;
                     if (p.ntaps > 1) { tap = kb / kb_per_tap; kin = (kb - tap * kb_per_tap) * TC_BK; shift = p.tap_rows[tap]; }
-                    tma_load_4d(sA + s * Cfg::A_BYTES, &map_a, &full_bar[s], kin, m0 + shift, z1, z0);
+                    uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                    tma_load_4d(st, &map_a, &full_bar[s], kin, m0 + shift, z1, z0);
+                    if constexpr (SPLIT) tma_load_4d(st + OFF_A_LO, &map_a_lo, &full_bar[s], kin, m0 + shift, z1, z0);
                     if (!p.trans_b) {
-                        tma_load_4d(sB + s * Cfg::B_BYTES, &map_b, &full_bar[s], kb * TC_BK, n0, z1, z0);
+                        tma_load_4d(st + OFF_B, &map_b, &full_bar[s], kb * TC_BK, n0, z1, z0);
+                        if constexpr (SPLIT) tma_load_4d(st + OFF_B_LO, &map_b_lo, &full_bar[s], kb * TC_BK, n0, z1, z0);
                     } else {
                         // B is [K, N]: boxes of 64 (n) x 64 (k); one box per 64 columns of the tile
 #pragma unroll
-                        for (int j = 0; j < (BN + 63) / 64; ++j)
-                            tma_load_4d(sB + s * Cfg::B_BYTES + j * (64 * 128), &map_b, &full_bar[s], n0 + j * 64, kb * TC_BK, z1, z0);
+                        for (int j = 0; j < (BN + 63) / 64; ++j) {
+                            tma_load_4d(st + OFF_B + j * (64 * 128), &map_b, &full_bar[s], n0 + j * 64, kb * TC_BK, z1, z0);
+                            if constexpr (SPLIT) tma_load_4d(st + OFF_B_LO + j * (64 * 128), &map_b_lo, &full_bar[s], n0 + j * 64, kb * TC_BK, z1, z0);
+                        }
                     }
                 }
             }
@@ -219,24 +240,36 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __
             idesc |= (uint32_t)(TC_BM >> 4) << 24;
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
+                const uint32_t acc = tcount % Cfg::ACC_STAGES, acc_ph = (tcount / Cfg::ACC_STAGES) & 1;
                 mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);          // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
+                const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+                    const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    // k-steps that lie entirely beyond K hold TMA zero fill only: skip them (K = 24, 144, 1377 ...)
+                    const int krem = p.ntaps > 1 ? TC_BK : p.K - kb * TC_BK;        // taps are whole k-blocks
+                    const int ksteps = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
-                        // K-major SW128: 8-row groups are 1024 B apart (SBO); a K step of 16 elements = +32 B inside the atom
-                        uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, 1024);
-                        uint64_t bdesc = p.trans_b ? make_smem_desc(b_addr + k * 2048, 64 * 128, 1024)     // MN-major: +2 k-groups
-                                                   : make_smem_desc(b_addr + k * 32, 16, 1024);
-                        umma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0);
+                        if (k < ksteps) {
+                            // K-major SW128: 8-row groups are 1024 B apart (SBO); a K step of 16 elements = +32 B inside the atom
+                            const uint32_t koff_a = k * 32, koff_b = p.trans_b ? k * 2048 : k * 32;   // MN-major B: +2 k-groups
+                            const uint32_t lbo_b = p.trans_b ? 64 * 128 : 16;
+                            const uint64_t a_hi = make_smem_desc(st + koff_a, 16, 1024);
+                            const uint64_t b_hi = make_smem_desc(st + OFF_B + koff_b, lbo_b, 1024);
+                            const uint32_t accum = (kb | k) != 0;
+                            umma_f16(tmem_d, a_hi, b_hi, idesc, accum);
+                            if constexpr (SPLIT) {
+                                const uint64_t a_lo = make_smem_desc(st + OFF_A_LO + koff_a, 16, 1024);
+                                const uint64_t b_lo = make_smem_desc(st + OFF_B_LO + koff_b, lbo_b, 1024);
+                                umma_f16(tmem_d + BN, a_hi, b_lo, idesc, accum);
+                                umma_f16(tmem_d + BN, a_lo, b_hi, idesc, 1u);
+                            }
+                        }
                     }
                     umma_commit(&empty_bar[s]);          // frees the smem slot when these MMAs retire
                 }
@@ -253,9 +286,10 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __
             const int z = tile / tiles_per_z, r = tile - z * tiles_per_z;
             const int nt = r / p.tiles_m, mt = r - nt * p.tiles_m;
             const int m0 = mt * TC_BM, n0 = nt * BN, z0 = z / p.batch1, z1 = z - z0 * p.batch1;
-            const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
+            const uint32_t acc = tcount % Cfg::ACC_STAGES, acc_ph = (tcount / Cfg::ACC_STAGES) & 1;
             Epilogue e = p.epi;
             e.C = (char*)e.C + (z0 * p.sc0 + z1 * p.sc1) * dtype_size(e.dtype_c);
+            if (e.C_lo) e.C_lo = (char*)e.C_lo + (z0 * p.sc0 + z1 * p.sc1) * 2;
             if (e.R) e.R = (const char*)e.R + (z0 * p.sr0 + z1 * p.sr1) * dtype_size(e.dtype_r);
             if (e.norm_a) e.norm_a += z0 * p.sna0;
             if (e.norm_b) e.norm_b += z0 * p.snb0;
@@ -273,13 +307,22 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __
             const int nlim = min(p.N, n0 + BN);                  // columns of this tile (BN need not be a multiple of 32)
             const int m = m0 + q * 32 + lane;
             const int64_t orow = m < p.M ? e.map_row(m) : -1;
-            const bool vec_ok = (e.ldc * dtype_size(e.dtype_c)) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.C) % 16 == 0);
+            const int es_c = dtype_size(e.dtype_c);
+            const bool vec_ok = (e.ldc * es_c) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.C) % 16 == 0) &&
+                                (e.dtype_c != RB_F16S || reinterpret_cast<uintptr_t>(e.C_lo) % 16 == 0);
 #pragma unroll 1
             for (int cb = half * 32; cb < BN; cb += 8 * Cfg::EPI_WARPS) {
                 if (n0 + cb >= nlim) break;                     // warp-uniform
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cb, v);
-                if (orow < 0) continue;
+                // all 32 lanes take part in the TMEM loads (.sync.aligned); rows that are not stored are masked below
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + cb, v);
+                if constexpr (SPLIT) {
+                    float w[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + BN + cb, w);
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaf(w[j], 1.0f / 2048.0f, v[j]);
+                }
+                if (orow >= 0) {
                 const int nb = n0 + cb;
                 const bool full = nb + 32 <= nlim;
                 // every branch below is warp-uniform: the per-element work is straight-line code
@@ -344,6 +387,33 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __
                                 for (int t = 0; t < 4; ++t) if (nb + 4 * j + t < nlim) dst[4 * j + t] = v[4 * j + t];
                             }
                         }
+                    } else if (e.dtype_c == RB_F16S) {
+                        // split-pair output: hi = fp16(v), lo = fp16((v - hi) * 2^11) into two planes of the same pitch
+                        uint16_t* dhi = (uint16_t*)e.C + orow * e.ldc + nb;
+                        uint16_t* dlo = (uint16_t*)e.C_lo + orow * e.ldc + nb;
+    #pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t wh[4], wl[4];
+    #pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float x0 = v[8 * j + 2 * t], x1 = v[8 * j + 2 * t + 1];
+                                const __half2 h = __floats2half2_rn(x0, x1);
+                                const float2 hf = __half22float2(h);
+                                const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+                                wh[t] = *reinterpret_cast<const uint32_t*>(&h); wl[t] = *reinterpret_cast<const uint32_t*>(&l);
+                            }
+                            if (nb + 8 * j + 8 <= nlim) {
+                                *reinterpret_cast<uint4*>(dhi + 8 * j) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                                *reinterpret_cast<uint4*>(dlo + 8 * j) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                            } else {
+    #pragma unroll
+                                for (int t = 0; t < 8; ++t)
+                                    if (nb + 8 * j + t < nlim) {
+                                        dhi[8 * j + t] = (uint16_t)(wh[t >> 1] >> (16 * (t & 1)));
+                                        dlo[8 * j + t] = (uint16_t)(wl[t >> 1] >> (16 * (t & 1)));
+                                    }
+                            }
+                        }
                     } else {
                         uint16_t* dst = (uint16_t*)e.C + orow * e.ldc + nb;
     #pragma unroll
@@ -366,8 +436,10 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) gemm_tc_kernel(const __
                 } else {
     #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (nb + j < nlim) store_any(e.C, orow * e.ldc + nb + j, e.dtype_c, v[j]);
+                        if (nb + j < nlim) store_split_any(e.C, e.C_lo, orow * e.ldc + nb + j, e.dtype_c, v[j]);
                 }
+                }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -415,25 +487,28 @@ static int make_map(CUtensorMap* map, const void* base, int is_bf16, uint64_t in
     return 0;
 }
 
+struct TcMaps { CUtensorMap a, b, a_lo, b_lo; };
+
 static int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[64] = {};
+    const int dev = current_device() & 63;
+    if (!n[dev]) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
-template <int BN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, int zdim, cudaStream_t st) {
-    using Cfg = TcCfg<BN>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+template <int BN, bool SPLIT>
+static int launch_tc(const TcMaps& maps, TcParams& p, int zdim, cudaStream_t st) {
+    using Cfg = TcCfg<BN, SPLIT>;
+    // function attributes are per device: one flag per device ordinal (several engines on different GPUs in one process)
+    static bool configured[64] = {};
+    const int dev = current_device();
+    if (!configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         RB_REQUIRE(e == cudaSuccess, "gemm_tc: cannot set %d bytes of dynamic shared memory: %s", Cfg::SMEM, cudaGetErrorString(e));
-        configured = true;
+        configured[dev & 63] = true;
     }
     p.tiles_m = (p.M + TC_BM - 1) / TC_BM;
     p.tiles_n = (p.N + BN - 1) / BN;
@@ -448,14 +523,29 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = rb::pdl_mode() == 1 ? 0 : 1;
-    cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, ma, mb, (const TcParams)p);
+    cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, SPLIT>, maps.a, maps.b, maps.a_lo, maps.b_lo, (const TcParams)p);
     if (err != cudaSuccess) { set_error("gemm_tc: launch failed: %s", cudaGetErrorString(err)); return 1; }
     return check_launch("gemm_tc");
 }
 
+template <bool SPLIT>
+static int dispatch_tc(int BN, const TcMaps& maps, TcParams& p, int zdim, cudaStream_t st) {
+    switch (BN) {
+        case 32: return launch_tc<32, SPLIT>(maps, p, zdim, st);
+        case 64: return launch_tc<64, SPLIT>(maps, p, zdim, st);
+        case 128: return launch_tc<128, SPLIT>(maps, p, zdim, st);
+        case 144: return launch_tc<144, SPLIT>(maps, p, zdim, st);
+        case 192: return launch_tc<192, SPLIT>(maps, p, zdim, st);
+        default: return launch_tc<256, SPLIT>(maps, p, zdim, st);
+    }
+}
+
 int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
-    RB_REQUIRE(a->dtype_ab == RB_F16 || a->dtype_ab == RB_BF16, "gemm_tc: operands must be fp16/bf16 (got %d)", a->dtype_ab);
+    RB_REQUIRE(a->dtype_ab == RB_F16 || a->dtype_ab == RB_BF16 || a->dtype_ab == RB_F16S, "gemm_tc: operands must be fp16/bf16/split-fp16 (got %d)", a->dtype_ab);
     RB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "gemm_tc: empty problem");
+    const bool split = a->dtype_ab == RB_F16S;
+    RB_REQUIRE(!split || (a->A_lo && a->B_lo), "gemm_tc: split-fp16 operands need A_lo and B_lo");
+    RB_REQUIRE(a->dtype_c != RB_F16S || a->C_lo, "gemm_tc: split-fp16 output needs C_lo");
     TcParams p;
     p.M = a->M; p.N = a->N; p.K = a->K;
     p.batch1 = a->batch1 > 0 ? a->batch1 : 1;
@@ -487,21 +577,19 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
     // (the threshold is in tiles: below ~100 wide tiles less than 2/3 of the SMs would have work; above it the wider tile wins
     // because these shapes are bound by L2 -> shared-memory operand traffic, which a 128-wide tile raises by a third)
     if (BN > 128 && ((int64_t)((a->M + 127) / 128) * ((a->N + BN - 1) / BN) * zdim) < 100) BN = 128;
-    CUtensorMap ma, mb;
-    if (make_map(&ma, a->A, p.is_bf16, p.ntaps > 1 ? p.k_per_tap : a->K, a_rows, a->lda, p.batch1, a->sa1, batch0, a->sa0, TC_BK, TC_BM)) return 1;
+    TcMaps maps;
+    const uint64_t a_inner = p.ntaps > 1 ? p.k_per_tap : a->K;
+    if (make_map(&maps.a, a->A, p.is_bf16, a_inner, a_rows, a->lda, p.batch1, a->sa1, batch0, a->sa0, TC_BK, TC_BM)) return 1;
+    if (split && make_map(&maps.a_lo, a->A_lo, 0, a_inner, a_rows, a->lda, p.batch1, a->sa1, batch0, a->sa0, TC_BK, TC_BM)) return 1;
     if (!a->trans_b) {
-        if (make_map(&mb, a->B, p.is_bf16, a->K, a->N, a->ldb, p.batch1, a->sb1, batch0, a->sb0, TC_BK, BN)) return 1;
+        if (make_map(&maps.b, a->B, p.is_bf16, a->K, a->N, a->ldb, p.batch1, a->sb1, batch0, a->sb0, TC_BK, BN)) return 1;
+        if (split && make_map(&maps.b_lo, a->B_lo, 0, a->K, a->N, a->ldb, p.batch1, a->sb1, batch0, a->sb0, TC_BK, BN)) return 1;
     } else {
-        if (make_map(&mb, a->B, p.is_bf16, a->N, a->K, a->ldb, p.batch1, a->sb1, batch0, a->sb0, 64, TC_BK)) return 1;
+        if (make_map(&maps.b, a->B, p.is_bf16, a->N, a->K, a->ldb, p.batch1, a->sb1, batch0, a->sb0, 64, TC_BK)) return 1;
+        if (split && make_map(&maps.b_lo, a->B_lo, 0, a->N, a->K, a->ldb, p.batch1, a->sb1, batch0, a->sb0, 64, TC_BK)) return 1;
     }
-    switch (BN) {
-        case 32: return launch_tc<32>(ma, mb, p, zdim, stream);
-        case 64: return launch_tc<64>(ma, mb, p, zdim, stream);
-        case 128: return launch_tc<128>(ma, mb, p, zdim, stream);
-        case 144: return launch_tc<144>(ma, mb, p, zdim, stream);
-        case 192: return launch_tc<192>(ma, mb, p, zdim, stream);
-        default: return launch_tc<256>(ma, mb, p, zdim, stream);
-    }
+    if (!split) { maps.a_lo = maps.a; maps.b_lo = maps.b; }
+    return split ? dispatch_tc<true>(BN, maps, p, zdim, stream) : dispatch_tc<false>(BN, maps, p, zdim, stream);
 }
 
 }  // namespace rb

@@ -309,10 +309,10 @@ __global__ void __launch_bounds__(128) local_corr_kernel(const LocalCorrParams p
 // the (8+4)x(16+4)x32 input tile is staged in shared memory as fp32; each thread owns one channel of one
 // output row and slides along x with the 25 weights in registers (100 LDS + 400 FMA per 16 outputs).
 // --------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool SPLIT = false>
 __global__ void __launch_bounds__(256) dwconv5x5_relu_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t ldi, int64_t ldo,
                                                              const float* __restrict__ wgt, int64_t ldw, const float* __restrict__ bias,
-                                                             int H, int W, int C, int tiles_x) {
+                                                             int H, int W, int C, int tiles_x, __half* __restrict__ out_lo = nullptr) {
     rb::pdl_wait();
     constexpr int TH = 8, TW = 16, CH = 32;
     __shared__ float tile[TH + 4][TW + 4][CH];
@@ -352,10 +352,18 @@ __global__ void __launch_bounds__(256) dwconv5x5_relu_kernel(const T* __restrict
     }
     const int yy = y0 + wid;
     if (!cok || yy >= H) return;
-    T* ob = out + ((int64_t)b * H * W + (int64_t)yy * W) * ldo + c;
+    if constexpr (SPLIT) {      // fp32 map in, RB_F16S pair out (the A operand of the split-fp16 pointwise GEMM)
+        const int64_t o0 = ((int64_t)b * H * W + (int64_t)yy * W) * ldo + c;
+        __half* oh = reinterpret_cast<__half*>(out);
 #pragma unroll
-    for (int i = 0; i < TW; ++i)
-        if (x0 + i < W) ob[(int64_t)(x0 + i) * ldo] = from_f<T>(fmaxf(acc[i], 0.f));
+        for (int i = 0; i < TW; ++i)
+            if (x0 + i < W) split_f16s(fmaxf(acc[i], 0.f), oh[o0 + (int64_t)(x0 + i) * ldo], out_lo[o0 + (int64_t)(x0 + i) * ldo]);
+    } else {
+        T* ob = out + ((int64_t)b * H * W + (int64_t)yy * W) * ldo + c;
+#pragma unroll
+        for (int i = 0; i < TW; ++i)
+            if (x0 + i < W) ob[(int64_t)(x0 + i) * ldo] = from_f<T>(fmaxf(acc[i], 0.f));
+    }
 }
 
 // (the 16-bit maps take the TMA-fed persistent kernel in dwconv_tma.cu)
@@ -717,9 +725,11 @@ extern "C" int romab200_dwconv5x5_relu(const rb_dwconv_args* a, void* stream) {
         ((uintptr_t)a->in) % 16 == 0 && ((uintptr_t)a->out) % 4 == 0) {
         return dwconv_tma(a, st);
     }
-    if (a->dtype == RB_F32) rb::launch_pdl(dwconv5x5_relu_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)a->in, (float*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
-    else if (a->dtype == RB_F16) rb::launch_pdl(dwconv5x5_relu_kernel<__half>, dim3(grid), dim3(256), 0, st, (const __half*)a->in, (__half*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
-    else rb::launch_pdl(dwconv5x5_relu_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x);
+    RB_REQUIRE(!a->out_lo || a->dtype == RB_F32, "dwconv: the RB_F16S output (out_lo) is for fp32 maps");
+    if (a->dtype == RB_F32 && a->out_lo) rb::launch_pdl(dwconv5x5_relu_kernel<float, true>, dim3(grid), dim3(256), 0, st, (const float*)a->in, (float*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x, (__half*)a->out_lo);
+    else if (a->dtype == RB_F32) rb::launch_pdl(dwconv5x5_relu_kernel<float, false>, dim3(grid), dim3(256), 0, st, (const float*)a->in, (float*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x, (__half*)nullptr);
+    else if (a->dtype == RB_F16) rb::launch_pdl(dwconv5x5_relu_kernel<__half, false>, dim3(grid), dim3(256), 0, st, (const __half*)a->in, (__half*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x, (__half*)nullptr);
+    else rb::launch_pdl(dwconv5x5_relu_kernel<__nv_bfloat16, false>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x, (__half*)nullptr);
     return check_launch("dwconv5x5_relu");
 }
 

@@ -6,8 +6,12 @@ and enqueues the whole of `forward_symmetric` / `forward` (`romatch/models/match
 (`torch.empty/zeros`) and streams only; every arithmetic step is one of our kernels.
 
 Precision regimes (`precision=`):
-  "fp32"        parity mode: fp32 operands and CUDA-core FFMA GEMMs everywhere, comparable to the
-                reference's CPU fp32 path at the 1e-4 level (tests/test_e2e_parity.py);
+  "fp32"        parity mode on the tensor cores: activations stay fp32 in HBM, every GEMM operand is carried as an
+                RB_F16S pair (fp16 hi plane + 2^11-scaled fp16 lo plane, 22 significand bits) and contracted by
+                three tcgen05 MMAs per k-step with fp32 accumulation in TMEM (gemm_tc.cu, SPLIT variant) — fp32-class
+                results, comparable to the reference's CPU fp32 path at the 1e-4 level
+                (tests/test_e2e_gpu.py::test_match_full_vs_reference_golden);
+  "fp32_simt"   the same arithmetic regime with CUDA-core FFMA GEMMs (gemm_simt.cu): the slow cross-check of "fp32";
   "fp16"/"bf16" fast mode, mirrors the reference's CUDA autocast regime (`utils.py:639-653`): 16-bit GEMM
                 operands on the tcgen05 tensor pipe with fp32 accumulation, fp32 residual stream,
                 LayerNorm, softmax statistics, GP solve, local-correlation accumulation, heads and
@@ -28,9 +32,10 @@ import torch.nn.functional as F
 
 from . import arch, cabi
 from .cabi import call
-from .packing import PackedWeights, pad8
+from .packing import PackedWeights, Split, pad8
 
-PRECISIONS = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+PRECISIONS = {"fp32": torch.float32, "fp32_simt": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+F16S = cabi.RB_F16S
 
 
 class Engine:
@@ -45,9 +50,12 @@ class Engine:
         self.precision = precision
         self.dtype = PRECISIONS[precision]
         self.dt = cabi.DTYPE_CODE[self.dtype]
+        self.split = precision == "fp32"         # fp32-class GEMMs on tcgen05 from RB_F16S operand pairs
+        self._lane = "main"                      # scratch buffers are per stream ("main" / "side")
         with torch.cuda.device(self.device):
-            self.w = PackedWeights(matcher_sd, dino_sd, self.device, self.dtype)
+            self.w = PackedWeights(matcher_sd, dino_sd, self.device, self.dtype, split=self.split)
         self._buf: Dict[tuple, torch.Tensor] = {}
+        self.generation = 0
         self._const: Dict[tuple, torch.Tensor] = {}
         self.debug: Optional[dict] = None        # set to {} to keep stage tensors (tests)
         self.use_flash_attn = True               # fused tcgen05 attention in the 16-bit modes (else QK^T / softmax / PV GEMMs)
@@ -83,8 +91,13 @@ class Engine:
             self._buf[key] = t
         return t
 
+    def sbuf(self, name, shape, zero=False) -> Split:
+        """A cached RB_F16S buffer: two fp16 planes of `shape`."""
+        return Split(self.buf(name + ".hi", shape, torch.float16, zero), self.buf(name + ".lo", shape, torch.float16, zero))
+
     def free_buffers(self):
         self._buf.clear()
+        self.generation += 1       # captured CUDA graphs hold raw pointers into these buffers: the matcher drops them
 
     def const(self, key, make):
         t = self._const.get(key)
@@ -128,12 +141,36 @@ class Engine:
         return self.const(("gpbasis", h, w), make)
 
     # ------------------------------------------------------------------ kernel wrappers
+    def split_pair(self, x, rows, cols, ld, name=None, row_norm=None) -> Split:
+        """fp32 matrix [rows, cols] (pitch ld) -> RB_F16S planes of the same pitch (a per-stream scratch pair unless named)."""
+        ldd = pad8(ld)
+        out = self.sbuf(name or f"split.{self._lane}.{rows * ldd}", (rows * ldd,))
+        call("romab200_split_f16s", "rb_split_pair_args", x=x, hi=out.hi, lo=out.lo, rows=rows, cols=cols, ldx=ld, ldd=ldd, row_norm=row_norm)
+        return out
+
     def gemm(self, A, B, C, M, N, K, lda, ldb, ldc, dtype_ab=None, dtype_c=None, **kw):
-        args = dict(A=A, B=B, C=C, M=M, N=N, K=K, lda=lda, ldb=ldb, ldc=ldc,
-                    dtype_ab=self.dt if dtype_ab is None else dtype_ab,
-                    dtype_c=self.dt if dtype_c is None else dtype_c,
-                    batch0=1, batch1=1, ntaps=1, alpha=1.0)
+        args = dict(M=M, N=N, K=K, lda=lda, ldb=ldb, ldc=ldc, batch0=1, batch1=1, ntaps=1, alpha=1.0)
         args.update(kw)
+        if self.split and dtype_ab is None:
+            # parity mode: operands as RB_F16S pairs.  Activations that no kernel wrote in that format are split here.
+            if not isinstance(A, Split):
+                assert args["batch0"] * args["batch1"] == 1 and lda % 8 == 0, "batched fp32 operands are split by the caller"
+                A = self.split_pair(A, args.get("a_rows") or M, K // args["ntaps"], lda)
+            if not isinstance(B, Split):
+                assert args["batch0"] * args["batch1"] == 1 and ldb % 8 == 0
+                tb = args.get("trans_b", 0)
+                B = self.split_pair(B, K if tb else N, N if tb else K, ldb, name=f"splitb.{self._lane}.{(K if tb else N) * ldb}")
+            dtype_ab = F16S
+            args.update(A=A.hi, A_lo=A.lo, B=B.hi, B_lo=B.lo)
+            if isinstance(C, Split):
+                args.update(C=C.hi, C_lo=C.lo)
+                dtype_c = F16S
+            else:
+                args.update(C=C)
+        else:
+            args.update(A=A, B=B, C=C)
+        args["dtype_ab"] = self.dt if dtype_ab is None else dtype_ab
+        args["dtype_c"] = self.dt if dtype_c is None else dtype_c
         if self.gemm_profile is None:
             call("romab200_gemm", "rb_gemm_args", **args)
             return
@@ -142,10 +179,14 @@ class Engine:
         call("romab200_gemm", "rb_gemm_args", **args)
         end.record()
         flops = 2.0 * M * N * K * args["batch0"] * args["batch1"]
-        self.gemm_profile.append(("simt" if args["dtype_ab"] == cabi.RB_F32 else "tcgen05", flops, start, end,
-                                  (M, N, K, args["batch0"] * args["batch1"]), args.get("epi", cabi.EPI_LINEAR)))
+        backend = {cabi.RB_F32: "simt", F16S: "tcgen05-split"}.get(args["dtype_ab"], "tcgen05")
+        self.gemm_profile.append((backend, flops, start, end, (M, N, K, args["batch0"] * args["batch1"]), args.get("epi", cabi.EPI_LINEAR)))
 
     def layernorm(self, x, y, gb, rows, cols, eps, dtype_y=None):
+        if isinstance(y, Split):
+            call("romab200_layernorm", "rb_layernorm_args", x=x, y=y.hi, y_lo=y.lo, gamma=gb[0], beta=gb[1], rows=rows, cols=cols,
+                 ldx=cols, ldy=cols, dtype_x=cabi.RB_F32, dtype_y=F16S, eps=eps)
+            return
         call("romab200_layernorm", "rb_layernorm_args", x=x, y=y, gamma=gb[0], beta=gb[1], rows=rows, cols=cols,
              ldx=cols, ldy=cols, dtype_x=cabi.RB_F32, dtype_y=self.dt if dtype_y is None else dtype_y, eps=eps)
 
@@ -155,20 +196,26 @@ class Engine:
 
     # ------------------------------------------------------------------ VGG19-BN (encoders.py:17-27)
     def vgg(self, image: torch.Tensor, tag: str):
-        """image [E,3,H,W] fp32 -> {s: zero-padded channels-last tap [E, H/s+2, W/s+2, C_s]} for s in 1,2,4,8."""
+        """image [E,3,H,W] fp32 -> {s: zero-padded channels-last tap [E, H/s+2, W/s+2, C_s]} for s in 1,2,4,8.
+        In the parity mode the maps are RB_F16S pairs (every consumer is a GEMM or the max-pool)."""
         E, _, H, W = image.shape
         taps = {}
         layers = self.w.vgg
         h, w = H, W
-        cur = self.buf(f"vgg{tag}.s1.in", (E, h + 2, w + 2, 64), zero=True)
-        call("romab200_conv3x3_first", "rb_conv_first_args", image=image, out=cur, weight=layers[0]["w"], bias=layers[0]["b"],
-             batch=E, height=h, width=w, cout=64, dtype_out=self.dt)
+        mk = (lambda name, shape: self.sbuf(name, shape, zero=True)) if self.split else (lambda name, shape: self.buf(name, shape, zero=True))
+        cur = mk(f"vgg{tag}.s1.in", (E, h + 2, w + 2, 64))
+        if self.split:
+            call("romab200_conv3x3_first", "rb_conv_first_args", image=image, out=cur.hi, out_lo=cur.lo, weight=layers[0]["w"], bias=layers[0]["b"],
+                 batch=E, height=h, width=w, cout=64, dtype_out=F16S)
+        else:
+            call("romab200_conv3x3_first", "rb_conv_first_args", image=image, out=cur, weight=layers[0]["w"], bias=layers[0]["b"],
+                 batch=E, height=h, width=w, cout=64, dtype_out=self.dt)
         li, scale = 1, 1
         for nconv in (1, 2, 4, 4):                              # convs left in each stage after conv0
             for j in range(nconv):
                 L = layers[li]
                 li += 1
-                nxt = self.buf(f"vgg{tag}.s{scale}.p{j % 2}", (E, h + 2, w + 2, L["cout"]), zero=True)
+                nxt = mk(f"vgg{tag}.s{scale}.p{j % 2}", (E, h + 2, w + 2, L["cout"]))
                 rows = E * (h + 2) * (w + 2)
                 taps_rows = [(ky - 1) * (w + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
                 self.gemm(cur, L["w"], nxt, rows, L["cout"], 9 * L["cin"], L["cin"], 9 * L["cin"], L["cout"],
@@ -179,9 +226,13 @@ class Engine:
             if scale == 8:
                 break
             c = layers[li - 1]["cout"]
-            pooled = self.buf(f"vgg{tag}.s{scale * 2}.in", (E, h // 2 + 2, w // 2 + 2, c), zero=True)
-            call("romab200_maxpool2x2_padded", "rb_maxpool_args", **{"in": cur}, out=pooled, batch=E, height=h, width=w,
-                 channels=c, dtype=self.dt)
+            pooled = mk(f"vgg{tag}.s{scale * 2}.in", (E, h // 2 + 2, w // 2 + 2, c))
+            if self.split:
+                call("romab200_maxpool2x2_padded", "rb_maxpool_args", **{"in": cur.hi}, in_lo=cur.lo, out=pooled.hi, out_lo=pooled.lo,
+                     batch=E, height=h, width=w, channels=c, dtype=F16S)
+            else:
+                call("romab200_maxpool2x2_padded", "rb_maxpool_args", **{"in": cur}, out=pooled, batch=E, height=h, width=w,
+                     channels=c, dtype=self.dt)
             cur, h, w, scale = pooled, h // 2, w // 2, scale * 2
         return taps
 
@@ -196,9 +247,23 @@ class Engine:
                      heads=heads, head_dim=d, dtype=self.dt)
             return
         npad = pad8(N)
+        ld = 3 * dim
+        if self.split:
+            # parity mode: q, k, v, the probabilities and the result are RB_F16S pairs; scores are fp32.  The 1/sqrt(d) scale
+            # rides on the QK^T epilogue like below.
+            S = self.buf(f"attn.scores.{tag}", (Bn, heads, N, npad), dtype=torch.float32)
+            P = self.sbuf(f"attn.probs.{tag}", (Bn, heads, N, npad))
+            q, k, v = qkv, qkv.at(dim), qkv.at(2 * dim)
+            with self.stage(f"  attn.{tag}"):
+                self.gemm(q, k, S, N, N, d, ld, ld, npad, batch0=Bn, batch1=heads, alpha=1.0 / math.sqrt(d), dtype_c=cabi.RB_F32,
+                          sa0=N * ld, sa1=d, sb0=N * ld, sb1=d, sc0=heads * N * npad, sc1=N * npad)
+                call("romab200_softmax_rows", "rb_softmax_args", s=S, rows=Bn * heads * N, cols=N, lds=npad, dtype=cabi.RB_F32, scale=1.0,
+                     out_hi=P.hi, out_lo=P.lo, ldo=npad)
+                self.gemm(P, v, out, N, d, N, npad, ld, dim, trans_b=1, batch0=Bn, batch1=heads,
+                          sa0=heads * N * npad, sa1=N * npad, sb0=N * ld, sb1=d, sc0=N * dim, sc1=d)
+            return
         sdt = self.dtype
         S = self.buf(f"attn.scores.{tag}", (Bn, heads, N, npad), dtype=sdt)
-        ld = 3 * dim
         es = qkv.element_size()
         q_ptr, k_ptr, v_ptr = qkv.data_ptr(), qkv.data_ptr() + dim * es, qkv.data_ptr() + 2 * dim * es
         # the 1/sqrt(d) scale rides on the QK^T epilogue so that 16-bit scores cannot overflow
@@ -212,10 +277,11 @@ class Engine:
     def block(self, x, blk, Bn, N, dim, heads, mlp, eps, tag):
         """pre-LN transformer block on the fp32 residual stream x [Bn*N, dim] (block.py:82-107)."""
         rows = Bn * N
-        xn = self.buf(f"blk.xn.{tag}", (rows, dim))
-        qkv = self.buf(f"blk.qkv.{tag}", (rows, 3 * dim))
-        att = self.buf(f"blk.att.{tag}", (rows, dim))
-        hid = self.buf(f"blk.hid.{tag}", (rows, mlp))
+        mk = self.sbuf if self.split else self.buf       # parity mode: every GEMM operand of the block is an RB_F16S pair
+        xn = mk(f"blk.xn.{tag}", (rows, dim))
+        qkv = mk(f"blk.qkv.{tag}", (rows, 3 * dim))
+        att = mk(f"blk.att.{tag}", (rows, dim))
+        hid = mk(f"blk.hid.{tag}", (rows, mlp))
         self.layernorm(x, xn, blk["ln1"], rows, dim, eps)
         self.gemm(xn, blk["qkv_w"], qkv, rows, 3 * dim, dim, dim, dim, 3 * dim, bias=blk["qkv_b"])
         self.attention(qkv, att, Bn, N, heads, dim, tag)
@@ -284,7 +350,12 @@ class Engine:
         stride_w = (n + nrhs) * ldw
         # K_yy + sigma*I for every image (its own features): exp((cos-1)/T)   (matcher.py:191-200, 298, 301)
         tc_kernel = self.dtype != torch.float32 and self.gp_tensor_core
-        if tc_kernel:
+        xs = None
+        if self.split:
+            # all-pairs CosKernel on tcgen05 with fp32-class accuracy: the L2-normalised rows as an RB_F16S pair
+            with self.stage("  gp.split"):
+                xs = self.split_pair(p16, E * n, cf, cf, name="gp.xs", row_norm=norms)
+        elif tc_kernel:
             # all-pairs CosKernel on the f16 tensor pipe with fp32-class accuracy: L2-normalised rows split into fp16
             # hi/lo parts, A' = [hi|lo|hi], B' = [hi|hi|lo]  ->  A'.B'^T = hi.hi + lo.hi + hi.lo  (K' = 3*512)
             xa = self.buf("gp.split_a", (E * n, 3 * cf), dtype=torch.float16)
@@ -293,7 +364,10 @@ class Engine:
                 call("romab200_split_f16x3", "rb_split_args", x=p16, dst=xa, rows=E * n, cols=cf, ldx=cf, ldd=3 * cf, row_norm=norms, layout_b=0)
                 call("romab200_split_f16x3", "rb_split_args", x=p16, dst=xb, rows=E * n, cols=cf, ldx=cf, ldd=3 * cf, row_norm=norms, layout_b=1)
         with self.stage("  gp.kyy"):
-            if tc_kernel:
+            if self.split:
+                self.gp_kernel_matrix_split(xs, xs, norms, norms, Wk, n, cf, ldw, batch=E, sa=n * cf, sb=n * cf, sc=stride_w,
+                                            sna=n, snb=n, diag=arch.GP_SIGMA_NOISE)
+            elif tc_kernel:
                 self.gp_kernel_matrix_tc(xa, xb, norms, norms, Wk, n, cf, ldw, batch=E, sa=n * 3 * cf, sb=n * 3 * cf, sc=stride_w,
                                          sna=n, snb=n, diag=arch.GP_SIGMA_NOISE)
             else:
@@ -309,11 +383,25 @@ class Engine:
             call("romab200_gp_solve", "rb_gp_solve_args", W=Wk, n=n, nrhs=nrhs, batch=E, ldw=ldw, stride=stride_w,
                  workspace=ws if self.gp_algo else None, workspace_bytes=ws_bytes if self.gp_algo else 0, algo=self.gp_algo)
         # K_xy and mu = K_xy @ alpha for every decoder item: query image i, support image (i + b) % E
-        kxy = self.buf("gp.kxy", (D, n, ldw), dtype=torch.float32)
         dim = arch.DEC_DIM
         tokens = self.buf("dec.tokens_in", (D * n, dim))
         es = tokens.element_size()
         halves = [(0, b, b)] if D == b else [(0, b, b), (b, b, 0)]     # (first item, count, first support image)
+        if self.split:
+            kxy = self.sbuf("gp.kxy", (D, n, ldw))
+            alpha = self.sbuf("gp.alpha", (E, nrhs, ldw))
+            with self.stage("  gp.kxy+mu"):
+                for e in range(E):          # alpha^T = rows n.. of every solved workspace
+                    call("romab200_split_f16s", "rb_split_pair_args", x=Wk.data_ptr() + (e * stride_w + n * ldw) * 4,
+                         hi=alpha.at(e * nrhs * ldw).hi, lo=alpha.at(e * nrhs * ldw).lo, rows=nrhs, cols=n, ldx=ldw, ldd=ldw)
+                for i0, cnt, y0 in halves:
+                    self.gp_kernel_matrix_split(xs.at(i0 * n * cf), xs.at(y0 * n * cf), norms.data_ptr() + i0 * n * 4, norms.data_ptr() + y0 * n * 4,
+                                                kxy.at(i0 * n * ldw), n, cf, ldw, batch=cnt, sa=n * cf, sb=n * cf, sc=n * ldw, sna=n, snb=n, diag=0.0)
+                    self.gemm(kxy.at(i0 * n * ldw), alpha.at(y0 * nrhs * ldw), tokens.data_ptr() + i0 * n * dim * es, n, nrhs, n, ldw, ldw, dim,
+                              batch0=cnt, sa0=n * ldw, sb0=nrhs * ldw, sc0=n * dim)
+            halves = []
+        else:
+            kxy = self.buf("gp.kxy", (D, n, ldw), dtype=torch.float32)
         for i0, cnt, y0 in halves:
           with self.stage("  gp.kxy+mu"):
             if tc_kernel:
@@ -338,8 +426,11 @@ class Engine:
         with self.stage("  dec.blocks"):
             for blk in self.w.dec:
                 self.block(x, blk, D, n, dim, arch.DEC_HEADS, arch.DEC_MLP, arch.DEC_LN_EPS, "dec")
-        xa = self.buf("dec.xa", (D * n, dim))
-        self.copy2d(x, xa, D * n, dim, dim, dim, f32, self.dt)
+        if self.split:
+            xa = x                                  # split into an RB_F16S pair by the GEMM wrapper
+        else:
+            xa = self.buf("dec.xa", (D * n, dim))
+            self.copy2d(x, xa, D * n, dim, dim, dim, f32, self.dt)
         ldl = pad8(arch.CLS_OUT)
         logits = self.buf("dec.logits", (D * n, ldl), dtype=torch.float32)
         with self.stage("  dec.to_out+cls"):
@@ -359,6 +450,12 @@ class Engine:
                   sa0=sa, sb0=sb, sc0=sc, epi=cabi.EPI_COSKERNEL, norm_a=na, norm_b=nb, sna0=sna, snb0=snb,
                   eps=arch.GP_COS_EPS, inv_t=1.0 / arch.GP_TEMPERATURE, diag_add=diag, cos_normalized=0)
 
+    def gp_kernel_matrix_split(self, A: Split, B: Split, na, nb, C, n, cf, ldc, batch, sa, sb, sc, sna, snb, diag):
+        """Same contraction on tcgen05 from RB_F16S pairs of the L2-normalised rows (cos_normalized=1); C fp32 or a pair."""
+        self.gemm(A, B, C, n, n, cf, cf, cf, ldc, dtype_c=cabi.RB_F32, batch0=batch,
+                  sa0=sa, sb0=sb, sc0=sc, epi=cabi.EPI_COSKERNEL, norm_a=na, norm_b=nb, sna0=sna, snb0=snb,
+                  eps=arch.GP_COS_EPS, inv_t=1.0 / arch.GP_TEMPERATURE, diag_add=diag, cos_normalized=1)
+
     def gp_kernel_matrix_tc(self, A, B, na, nb, C, n, cf, ldc, batch, sa, sb, sc, sna, snb, diag):
         """Same contraction on tcgen05 from the split fp16 operands (pre-normalised rows: cos_normalized=1)."""
         self.gemm(A, B, C, n, n, 3 * cf, 3 * cf, 3 * cf, ldc, dtype_ab=cabi.RB_F16, dtype_c=cabi.RB_F32, batch0=batch,
@@ -370,7 +467,7 @@ class Engine:
         R = self.w.refiner[s]
         spec, c, cp = R["spec"], R["c"], R["cp"]
         d = self.buf(f"ref.d.{tag}", (D * h * w, cp), zero=True)
-        t = self.buf(f"ref.t.{tag}", (D * h * w, cp), zero=True)
+        t = None if self.split else self.buf(f"ref.t.{tag}", (D * h * w, cp), zero=True)
         r = spec.radius
         with self.stage(f"  prologue{s}.{tag[:2]}"):
           call("romab200_refiner_prologue", "rb_refiner_prologue_args", feat=feat, ldf=ldf, n_img=E, y_shift=b,
@@ -394,6 +491,13 @@ class Engine:
                 call("romab200_refiner_block_c144", "rb_refiner_block_c144_args", **{"in": d}, out=t, ld=cp, dw_weight=blk["dw_w"], ldw=cp,
                      dw_bias=blk["dw_b"], pw_weight=blk["pw_w"], ld_pw=cp, pw_bias=blk["pw_b"], batch=D, h=h, w=w, c=c, dtype=self.dt)
                 d, t = t, d
+        elif self.split:
+            # parity mode: fp32 maps; the depthwise kernel writes its result as the RB_F16S A operand of the pointwise GEMM
+            ts = self.sbuf(f"ref.ts.{tag}", (D * h * w, cp), zero=True)
+            for blk in R["blocks"]:
+                call("romab200_dwconv5x5_relu", "rb_dwconv_args", **{"in": d}, out=ts.hi, out_lo=ts.lo, ldi=cp, ldo=cp, weight=blk["dw_w"], ldw=cp,
+                     bias=blk["dw_b"], batch=D, h=h, w=w, c=c, dtype=cabi.RB_F32)
+                self.gemm(ts, blk["pw_w"], d, rows, c, c, cp, cp, cp, bias=blk["pw_b"])
         else:
             for blk in R["blocks"]:
                 call("romab200_dwconv5x5_relu", "rb_dwconv_args", **{"in": d}, out=t, ldi=cp, ldo=cp, weight=blk["dw_w"], ldw=cp,
@@ -493,6 +597,7 @@ class Engine:
                 vit = self.dinov2(images)
             side.wait_stream(main)
             with torch.cuda.stream(side):
+                self._lane = "side"
                 cnn_lo = self.encode_cnn(images, "lo")
                 ev_lo = torch.cuda.Event()
                 ev_lo.record(side)
@@ -500,6 +605,7 @@ class Engine:
                     cnn_hi = self.encode_cnn(images_hi, "up")
                     ev_hi = torch.cuda.Event()
                     ev_hi.record(side)
+                self._lane = "main"
         hs, ws = images.shape[-2:]
         state, states, sizes = self.run_pass(images, b, symmetric, False, scale_lo, cnn=cnn_lo, cnn_ready=ev_lo, vit=vit)
         coarse = states[16] if attenuate else None

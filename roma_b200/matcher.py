@@ -54,6 +54,11 @@ class RegressionMatcher:
     def _get_device(self):
         return self.engine.device
 
+    def free_buffers(self):
+        """Release every cached activation buffer and the CUDA graphs recorded over them."""
+        self._graphs.clear()
+        self.engine.free_buffers()
+
     def get_output_resolution(self):
         if not self.upsample_preds:
             return self.h_resized, self.w_resized
@@ -155,12 +160,16 @@ class RegressionMatcher:
         key = (b, hs, ws, ho if a_h is not None else 0, wo if a_h is not None else 0, symmetric, attenuate, float(scale_factor),
                tuple(self.upsample_res))
         entry = self._graphs.get(key) if use_graph else None
+        if entry is not None and entry["generation"] != eng.generation:
+            # Engine.free_buffers() released the activation buffers this graph's kernels point into: re-record
+            del self._graphs[key]
+            entry = None
         if entry is None:
             images = torch.empty(2 * b, 3, hs, ws, dtype=torch.float32, device=dev)
             images_hi = torch.empty(2 * b, 3, ho, wo, dtype=torch.float32, device=dev) if a_h is not None else None
             warp = torch.empty(b, ho, wout, 4, dtype=torch.float32, device=dev)
             cert = torch.empty(b, ho, wout, dtype=torch.float32, device=dev)
-            entry = dict(images=images, images_hi=images_hi, warp=warp, cert=cert, graph=None, calls=0)
+            entry = dict(images=images, images_hi=images_hi, warp=warp, cert=cert, graph=None, calls=0, generation=eng.generation)
             if use_graph:
                 self._graphs[key] = entry
         entry["images"][:b].copy_(a_t, non_blocking=True)

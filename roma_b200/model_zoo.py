@@ -5,7 +5,8 @@
 Weights are state dicts in the reference's key layout; with `weights=None` the reference downloads them
 via `torch.hub` and so does this factory (there is no bundled checkpoint).  `amp_dtype` selects the
 arithmetic regime exactly as on the reference's CUDA path: float16 (default) / bfloat16 = 16-bit tensor-core
-operands with fp32 accumulation, float32 = the fp32 parity mode.
+operands with fp32 accumulation, float32 = the fp32 parity mode (fp32-class GEMMs on the tensor cores from split-fp16
+operand pairs; `fp32_backend` below selects the CUDA-core cross-check instead).
 """
 from __future__ import annotations
 
@@ -28,6 +29,10 @@ weight_urls = {
 }
 
 _PRECISION = {torch.float16: "fp16", torch.bfloat16: "bf16", torch.float32: "fp32"}
+# GEMM back-end of the amp_dtype=float32 parity mode: "tcgen05" (default) = split-fp16 operand pairs on the tensor cores
+# (fp32-class results); "simt" = CUDA-core FFMA GEMMs, kept as the slow cross-check.  Also settable with the environment
+# variable ROMA_B200_FP32_BACKEND (the factories keep the reference's signatures, so this is not a keyword argument).
+fp32_backend = None
 
 
 def roma_model(resolution, upsample_preds, device=None, weights=None, dinov2_weights=None,
@@ -43,7 +48,14 @@ def roma_model(resolution, upsample_preds, device=None, weights=None, dinov2_wei
     assert resolution[1] % 14 == 0, "Needs to be multiple of 14 for backbone"
     if amp_dtype not in _PRECISION:
         raise ValueError(f"unsupported amp_dtype {amp_dtype}")
-    engine = Engine(weights, dinov2_weights, device, precision=_PRECISION[amp_dtype])
+    precision = _PRECISION[amp_dtype]
+    if precision == "fp32":
+        import os
+        backend = fp32_backend or os.environ.get("ROMA_B200_FP32_BACKEND", "tcgen05")
+        if backend not in ("tcgen05", "simt"):
+            raise ValueError(f"fp32 back-end must be 'tcgen05' or 'simt', got {backend!r}")
+        precision = "fp32" if backend == "tcgen05" else "fp32_simt"
+    engine = Engine(weights, dinov2_weights, device, precision=precision)
     h, w = resolution
     return RegressionMatcher(engine, h=h, w=w, upsample_preds=upsample_preds, upsample_res=upsample_res,
                              symmetric=symmetric, attenuate_cert=attenuate_cert, sample_mode=sample_mode,

@@ -33,10 +33,45 @@ def fold_bn(w: torch.Tensor, b: torch.Tensor, sd: Dict[str, torch.Tensor], bn: s
     return w2.float(), b2.float()
 
 
-def _mat(w: torch.Tensor, dtype, device, pitch=None):
-    """[n, k] fp32 -> [n, pitch] compute-dtype matrix (zero padded along k)."""
+class Split:
+    """An RB_F16S matrix (include/romab200.h): fp16 hi plane + fp16 lo plane of identical geometry, value = hi + lo * 2^-11
+    with hi = fp16(x), lo = fp16((x - hi) * 2^11).  `hi` / `lo` are tensors, or raw device pointers (ints) for views."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def at(self, elems: int) -> "Split":
+        """The pair of planes starting `elems` elements further (2 bytes per element and plane)."""
+        ptr = lambda t: t if isinstance(t, int) else t.data_ptr()
+        return Split(ptr(self.hi) + 2 * elems, ptr(self.lo) + 2 * elems)
+
+    def join(self) -> torch.Tensor:
+        """fp32 reconstruction (tests / debug)."""
+        return self.hi.float() + self.lo.float() / 2048.0
+
+
+def split_f16s(w: torch.Tensor):
+    """fp32 tensor -> (hi, lo) fp16 planes of the RB_F16S format (the host twin of csrc/common.cuh::split_f16s)."""
+    w = w.float()
+    hi = w.to(torch.float16)
+    lo = ((w - hi.float()) * 2048.0).to(torch.float16)
+    return hi, lo
+
+
+def _mat(w: torch.Tensor, dtype, device, pitch=None, split=False):
+    """[n, k] fp32 -> [n, pitch] compute-dtype matrix (zero padded along k); an RB_F16S pair in the parity mode."""
     n, k = w.shape
     pitch = pitch or pad8(k)
+    if split:
+        hi, lo = split_f16s(w)
+        oh, ol = torch.zeros(n, pitch, dtype=torch.float16), torch.zeros(n, pitch, dtype=torch.float16)
+        oh[:, :k], ol[:, :k] = hi, lo
+        return Split(oh.to(device), ol.to(device))
     out = torch.zeros(n, pitch, dtype=dtype)
     out[:, :k] = w.to(dtype)
     return out.to(device)
@@ -49,21 +84,21 @@ def _vec(v: torch.Tensor, device):
 class PackedWeights:
     """All device-resident parameters of the path, keyed by stage."""
 
-    def __init__(self, matcher_sd: Dict[str, torch.Tensor], dino_sd: Dict[str, torch.Tensor], device, dtype: torch.dtype):
-        self.device, self.dtype = device, dtype
+    def __init__(self, matcher_sd: Dict[str, torch.Tensor], dino_sd: Dict[str, torch.Tensor], device, dtype: torch.dtype, split: bool = False):
+        self.device, self.dtype, self.split = device, dtype, split
         sd = {k: v.detach().cpu() for k, v in matcher_sd.items()}
         dd = {k: v.detach().cpu().float() for k, v in dino_sd.items()}
         self._check(sd, dd)
         self.vgg = self._pack_vgg(sd)
         self.proj = self._pack_proj(sd)
         self.vit = self._pack_blocks(dd, "blocks", arch.VIT_DEPTH, layerscale=True, qkv_bias=True)
-        self.vit_patch_w = _mat(dd["patch_embed.proj.weight"].flatten(1), dtype, device)       # [1024, 588 -> 592]
+        self.vit_patch_w = _mat(dd["patch_embed.proj.weight"].flatten(1), dtype, device, split=split)       # [1024, 588 -> 592]
         self.vit_patch_b = _vec(dd["patch_embed.proj.bias"], device)
         self.vit_cls = _vec(dd["cls_token"].reshape(-1), device)
         self.vit_pos_embed = dd["pos_embed"]                  # host fp32; interpolated per resolution by the engine
         self.vit_norm = (_vec(dd["norm.weight"], device), _vec(dd["norm.bias"], device))
         self.dec = self._pack_blocks(sd, "decoder.embedding_decoder.blocks", arch.DEC_DEPTH, layerscale=False, qkv_bias=False)
-        self.to_out_w = _mat(sd["decoder.embedding_decoder.to_out.weight"], dtype, device)
+        self.to_out_w = _mat(sd["decoder.embedding_decoder.to_out.weight"].float(), dtype, device, split=split)
         self.to_out_b = _vec(sd["decoder.embedding_decoder.to_out.bias"], device)
         self.gp_pos_w = sd["decoder.gps.16.pos_conv.weight"].float()          # host: the basis is a per-resolution constant
         self.gp_pos_b = sd["decoder.gps.16.pos_conv.bias"].float()
@@ -95,7 +130,7 @@ class PackedWeights:
                 layers.append(dict(w=w.reshape(cout, 27).contiguous().to(self.device), b=_vec(b, self.device), cin=cin, cout=cout))
             else:
                 wm = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin)        # K = (ky, kx, cin)
-                layers.append(dict(w=_mat(wm, self.dtype, self.device, pitch=9 * cin), b=_vec(b, self.device), cin=cin, cout=cout))
+                layers.append(dict(w=_mat(wm, self.dtype, self.device, pitch=9 * cin, split=self.split), b=_vec(b, self.device), cin=cin, cout=cout))
         return layers
 
     def _pack_proj(self, sd):
@@ -103,7 +138,7 @@ class PackedWeights:
         for s in arch.SCALES:
             w, b = fold_bn(sd[f"decoder.proj.{s}.0.weight"].float().flatten(1), sd[f"decoder.proj.{s}.0.bias"].float(),
                            sd, f"decoder.proj.{s}.1")
-            out[s] = dict(w=_mat(w, self.dtype, self.device), b=_vec(b, self.device))
+            out[s] = dict(w=_mat(w, self.dtype, self.device, split=self.split), b=_vec(b, self.device))
         return out
 
     def _pack_blocks(self, sd, prefix, depth, layerscale, qkv_bias):
@@ -112,15 +147,15 @@ class PackedWeights:
             p = f"{prefix}.{i}"
             blocks.append(dict(
                 ln1=(_vec(sd[f"{p}.norm1.weight"], self.device), _vec(sd[f"{p}.norm1.bias"], self.device)),
-                qkv_w=_mat(sd[f"{p}.attn.qkv.weight"].float(), self.dtype, self.device),
+                qkv_w=_mat(sd[f"{p}.attn.qkv.weight"].float(), self.dtype, self.device, split=self.split),
                 qkv_b=_vec(sd[f"{p}.attn.qkv.bias"], self.device) if qkv_bias else None,
-                proj_w=_mat(sd[f"{p}.attn.proj.weight"].float(), self.dtype, self.device),
+                proj_w=_mat(sd[f"{p}.attn.proj.weight"].float(), self.dtype, self.device, split=self.split),
                 proj_b=_vec(sd[f"{p}.attn.proj.bias"], self.device),
                 ls1=_vec(sd[f"{p}.ls1.gamma"], self.device) if layerscale else None,
                 ln2=(_vec(sd[f"{p}.norm2.weight"], self.device), _vec(sd[f"{p}.norm2.bias"], self.device)),
-                fc1_w=_mat(sd[f"{p}.mlp.fc1.weight"].float(), self.dtype, self.device),
+                fc1_w=_mat(sd[f"{p}.mlp.fc1.weight"].float(), self.dtype, self.device, split=self.split),
                 fc1_b=_vec(sd[f"{p}.mlp.fc1.bias"], self.device),
-                fc2_w=_mat(sd[f"{p}.mlp.fc2.weight"].float(), self.dtype, self.device),
+                fc2_w=_mat(sd[f"{p}.mlp.fc2.weight"].float(), self.dtype, self.device, split=self.split),
                 fc2_b=_vec(sd[f"{p}.mlp.fc2.bias"], self.device),
                 ls2=_vec(sd[f"{p}.ls2.gamma"], self.device) if layerscale else None,
             ))
@@ -139,7 +174,7 @@ class PackedWeights:
             pw = sd[f"{q}.3.weight"].float().flatten(1)
             blocks.append(dict(
                 dw_w=dwt.to(self.device), dw_b=_vec(db, self.device),
-                pw_w=_mat(pw, self.dtype, self.device, pitch=cp),
+                pw_w=_mat(pw, self.dtype, self.device, pitch=cp, split=self.split),
                 pw_b=_vec(sd[f"{q}.3.bias"], self.device),
                 # thin maps (C = 24) run the fused CUDA-core block: fp32 copy of the compute-dtype-rounded weights
                 # thin maps: the fused block kernel takes its pointwise weights as launch parameters, i.e. from host memory

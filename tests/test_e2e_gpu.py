@@ -12,11 +12,21 @@ from roma_b200 import synthetic  # noqa: E402
 TOL = 1e-4
 
 
-def build(weights, g, amp_dtype=torch.float32):
-    from roma_b200 import roma_outdoor
+BACKENDS = ["tcgen05", "simt"]       # GEMM back-ends of the fp32 parity mode: split-fp16 pairs on the tensor cores / CUDA-core FFMA
+
+
+def build(weights, g, amp_dtype=torch.float32, backend="tcgen05"):
+    from roma_b200 import model_zoo, roma_outdoor
     coarse, up, sym, upp = (int(v) for v in g["meta"][:4])
-    return roma_outdoor("cuda", weights=weights[0], dinov2_weights=weights[1], coarse_res=coarse,
-                        upsample_res=up or coarse, symmetric=bool(sym), upsample_preds=bool(upp), amp_dtype=amp_dtype)
+    model_zoo.fp32_backend = backend
+    try:
+        m = roma_outdoor("cuda", weights=weights[0], dinov2_weights=weights[1], coarse_res=coarse,
+                         upsample_res=up or coarse, symmetric=bool(sym), upsample_preds=bool(upp), amp_dtype=amp_dtype)
+    finally:
+        model_zoo.fp32_backend = None
+    if amp_dtype == torch.float32:
+        assert m.engine.precision == ("fp32" if backend == "tcgen05" else "fp32_simt")
+    return m
 
 
 def report(name, warp, cert, g, step=1):
@@ -27,11 +37,12 @@ def report(name, warp, cert, g, step=1):
     return ew, ec
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("name", ["small_sym_up", "small_nosym_up", "small_sym_noup", "small_b2_sym_up"])
-def test_match_small_vs_reference_golden(weights, name):
+def test_match_small_vs_reference_golden(weights, name, backend):
     g = load_golden(name)
     coarse, up, sym, upp, batch, seed, step = (int(v) for v in g["meta"])
-    model = build(weights, g)
+    model = build(weights, g, backend=backend)
     A, B, Ah, Bh = synthetic.make_pair(batch, coarse, up if upp else None, seed)
     warp, cert = model.match(A.cuda(), B.cuda(), im_A_high_res=None if Ah is None else Ah.cuda(),
                              im_B_high_res=None if Bh is None else Bh.cuda())
@@ -41,10 +52,11 @@ def test_match_small_vs_reference_golden(weights, name):
     assert ew <= TOL and ec <= TOL
 
 
-def test_stagewise_vs_reference_hooks(weights):
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_stagewise_vs_reference_hooks(weights, backend):
     """Stage tensors of the coarse pass against the tensors hooked out of the reference's own modules."""
     g = load_golden("small_sym_up")
-    model = build(weights, g)
+    model = build(weights, g, backend=backend)
     model.engine.debug = {}
     A, B, Ah, Bh = synthetic.make_pair(1, 112, 168, 1)
     model.match(A.cuda(), B.cuda(), im_A_high_res=Ah.cuda(), im_B_high_res=Bh.cuda())
@@ -118,16 +130,18 @@ def test_sample_statistics(weights):
 
 
 @pytest.mark.slow
-def test_match_full_vs_reference_golden(weights):
-    """560 -> 864 (BASELINE config 2 workload) against the sub-sampled reference output."""
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_match_full_vs_reference_golden(weights, backend):
+    """560 -> 864 (BASELINE config 2 workload) against the sub-sampled reference output, for both GEMM back-ends of the
+    parity mode; "tcgen05" (split-fp16 operand pairs on the tensor cores) is the mode bench.py reports."""
     g = load_golden("full_sym_up")
-    model = build(weights, g)
+    model = build(weights, g, backend=backend)
     A, B, Ah, Bh = synthetic.make_pair(1, 560, 864, 1)
     warp, cert = model.match(A.cuda(), B.cuda(), im_A_high_res=Ah.cuda(), im_B_high_res=Bh.cuda())
     assert warp.shape == (1, 864, 1728, 4)
-    ew, ec = report("full", warp, cert, g, step=8)
+    ew, ec = report(f"full {backend}", warp, cert, g, step=8)
     assert ew <= TOL and ec <= TOL
-    model.engine.free_buffers()
+    model.free_buffers()
 
 
 @pytest.mark.parametrize("amp", [torch.float16, torch.bfloat16])
@@ -160,4 +174,37 @@ def test_match_fast_mode_full(weights):
     print(f"[fast fp16 full] warp err: median {np.median(ew):.2e} p99 {np.percentile(ew, 99):.2e} max {ew.max():.2e} "
           f"frac>1e-3 {np.mean(ew > 1e-3):.4f}; cert err median {np.median(ec):.2e} p99 {np.percentile(ec, 99):.2e} max {ec.max():.2e}")
     assert np.median(ew) < 1e-3 and np.mean(ew > 5e-2) < 0.05
-    model.engine.free_buffers()
+    model.free_buffers()
+
+
+@pytest.mark.parametrize("amp,backend", [(torch.float32, "tcgen05"), (torch.float32, "simt"), (torch.float16, "tcgen05")])
+def test_repeated_calls_and_cuda_graph_replay(weights, amp, backend):
+    """Callers (and bench.py) use the path behind the first call: call 2 re-uses zero-initialised buffers that now hold
+    stale data, call 3+ replays the captured CUDA graph (PDL edges, side-stream fork/join, baked-in tensor maps).  Ten
+    calls alternating two input shapes and fresh inputs must equal an eager model (use_cuda_graph=False) exactly, and the
+    fp32 modes must stay on the goldens; free_buffers() between calls must not leave a graph pointing at freed memory."""
+    g = load_golden("small_sym_up")
+    graph_model = build(weights, g, amp_dtype=amp, backend=backend)
+    eager_model = build(weights, g, amp_dtype=amp, backend=backend)
+    eager_model.use_cuda_graph = False
+    shapes = [(112, 168), (168, 224)]
+    for call_idx in range(10):
+        coarse, up = shapes[call_idx % 2]
+        seed = 1 if call_idx in (4, 8) else 10 + call_idx        # call 4: graph replay of the golden input; call 8: re-capture after free_buffers()
+        A, B, Ah, Bh = synthetic.make_pair(1, coarse, up, seed)
+        for m in (graph_model, eager_model):
+            m.upsample_res = (up, up)
+            m.h_resized = m.w_resized = coarse
+        args = (A.cuda(), B.cuda())
+        kw = dict(im_A_high_res=Ah.cuda(), im_B_high_res=Bh.cuda())
+        w1, c1 = graph_model.match(*args, **kw)
+        w2, c2 = eager_model.match(*args, **kw)
+        assert torch.isfinite(w1).all() and torch.isfinite(c1).all()
+        dw, dc = (w1 - w2).abs().max().item(), (c1 - c2).abs().max().item()
+        assert dw <= 1e-6 and dc <= 1e-6, (call_idx, dw, dc)
+        if seed == 1 and coarse == 112 and amp == torch.float32:
+            ew, ec = report(f"call {call_idx}", w1, c1, g)
+            assert ew <= TOL and ec <= TOL
+        if call_idx == 5:
+            graph_model.engine.free_buffers()        # what user code can do: graphs recorded so far must not be replayed
+    assert any(e["graph"] is not None for e in graph_model._graphs.values())

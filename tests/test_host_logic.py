@@ -13,11 +13,11 @@ from roma_b200.packing import PackedWeights, fold_bn, pad8
 
 def test_library_exports_every_declared_symbol():
     lib = cabi.load_library()
-    assert lib.romab200_abi_version() == 2
+    assert lib.romab200_abi_version() == 3
     assert len(cabi.FUNCTIONS) >= 20
     for fn in cabi.FUNCTIONS:
         assert hasattr(lib, fn), fn
-    assert ctypes.sizeof(cabi.STRUCTS["rb_gemm_args"]) == 336
+    assert ctypes.sizeof(cabi.STRUCTS["rb_gemm_args"]) == 360
 
 
 def test_fold_bn_matches_batchnorm(weights):
@@ -67,8 +67,17 @@ class _Recorder:
         valid = {f for f, _ in cabi.STRUCT_FIELDS[struct]}
         assert set(kw) <= valid, (fn, set(kw) - valid)
         self.calls.append(fn)
-        es = {0: 4, 1: 2, 2: 2}
+        es = {0: 4, 1: 2, 2: 2, 3: 2}
         if fn == "romab200_gemm":
+            if kw["dtype_ab"] == cabi.RB_F16S:        # split pairs: the second planes have the same geometry
+                assert kw.get("A_lo") is not None and kw.get("B_lo") is not None
+                lo = dict(kw, A=kw["A_lo"], B=kw["B_lo"], A_lo=None, B_lo=None, dtype_ab=cabi.RB_F16)
+                if kw["dtype_c"] == cabi.RB_F16S:
+                    lo.update(C=kw["C_lo"], dtype_c=cabi.RB_F16)
+                self.calls.pop()
+                self(fn, struct, **{k: v for k, v in lo.items() if v is not None})
+            if kw["dtype_c"] == cabi.RB_F16S:
+                assert kw.get("C_lo") is not None
             b0, b1 = kw.get("batch0", 1), kw.get("batch1", 1)
             M, N, K = kw["M"], kw["N"], kw["K"]
             ea, ec = es[kw["dtype_ab"]], es[kw["dtype_c"]]
@@ -91,20 +100,23 @@ class _Recorder:
                 rows_out = M // (kw["pad_h"] * kw["pad_w"]) * (kw["pad_h"] - 2) * (kw["pad_w"] - 2)
             self._inside(kw["C"], (offc + (rows_out - 1) * kw["ldc"] + N) * ec, f"{fn}.C")
             assert kw["lda"] % 4 == 0 and kw["ldb"] % 4 == 0, "vector path wants 16-byte pitches"
+            if ea == 2:
+                assert kw["lda"] % 8 == 0 and kw["ldb"] % 8 == 0, "TMA wants 16-byte pitches"
         for k, v in kw.items():
             if isinstance(v, torch.Tensor):
                 assert v.is_contiguous(), (fn, k)
                 self._inside(v, 1, f"{fn}.{k}")
 
 
-@pytest.mark.parametrize("symmetric,upsample", [(True, True), (False, True), (True, False)])
-def test_engine_dry_run(weights, monkeypatch, symmetric, upsample):
+@pytest.mark.parametrize("symmetric,upsample,split", [(True, True, True), (True, True, False), (False, True, True), (True, False, False)])
+def test_engine_dry_run(weights, monkeypatch, symmetric, upsample, split):
     import roma_b200.engine as engine_mod
     rec = _Recorder()
     eng = engine_mod.Engine.__new__(engine_mod.Engine)
     eng.device = torch.device("cpu")
-    eng.precision, eng.dtype, eng.dt = "fp32", torch.float32, cabi.RB_F32
-    eng.w = PackedWeights(weights[0], weights[1], eng.device, torch.float32)
+    eng.precision, eng.dtype, eng.dt = "fp32" if split else "fp32_simt", torch.float32, cabi.RB_F32
+    eng.split, eng._lane, eng.generation = split, "main", 0
+    eng.w = PackedWeights(weights[0], weights[1], eng.device, torch.float32, split=split)
     eng._buf, eng._const, eng.debug, eng.profile, eng.gemm_profile, eng.use_flash_attn, eng.gp_algo = {}, {}, None, None, None, True, 2
     eng.overlap_cnn, eng._side, eng.gp_tensor_core, eng.fused_c144 = False, None, True, True
     for t in _tensors(eng.w):
@@ -145,6 +157,8 @@ def _tensors(obj):
     elif isinstance(obj, (list, tuple)):
         for v in obj:
             yield from _tensors(v)
+    elif hasattr(obj, "hi") and hasattr(obj, "lo"):          # packing.Split (RB_F16S pair)
+        yield from _tensors([obj.hi, obj.lo])
     elif hasattr(obj, "__dict__"):
         yield from _tensors(vars(obj))
 
