@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — pairs/s of RoMa dense match() (+ sample()) at 560 -> 864 on B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp16|bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|fp32_simt|fp16|bf16]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch of synthetic input: `roma_outdoor(...).match()` on
@@ -14,6 +14,10 @@ no data-path collective — pairs are independent).  Prints ONE JSO
              step's results (warp, certainty, sampled matches) read back D2H inside the timed region
   roofline   the dominant kernel (the GEMM back-end: tcgen05 in the 16-bit modes), algorithmic FLOPs of every
              launch / its CUDA-event time, both collected live during the timed steps
+  parity     max-abs error of this run's warp / certainty against tests/golden/full_sym_up.npz (the UNMODIFIED reference's
+             fp32 output for the seed-1 pair, every 8th pixel), computed live; the default precision is the one that meets
+             the 1e-4 bar: "fp32" = fp32-class GEMMs on tcgen05 from split-fp16 operand pairs
+  fast_mode  the same workload in the reference's CUDA autocast regime (fp16 operands), reported beside it with its error
   cpu_baseline  the CPU oracle (a port of the reference's fp32 CPU path) on this box's host cores, one pair
 --impl reference times that CPU path alone (the reference itself is pure Python/PyTorch and does not travel
 to the GPU box; `oracle/` is its validated restatement, bit-exact against it in the build container).
@@ -158,10 +162,12 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
-    amp = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.precision]
+    from roma_b200 import model_zoo
+    amp = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32, "fp32_simt": torch.float32}[args.precision]
     mw, dw = synthetic.make_weights(0)
+    model_zoo.fp32_backend = "simt" if args.precision == "fp32_simt" else "tcgen05"
     model = roma_outdoor(dev, weights=mw, dinov2_weights=dw, coarse_res=COARSE, upsample_res=UPSAMPLE, amp_dtype=amp)
-    del mw, dw
+    assert model.engine.precision == args.precision
     P = args.pairs_per_gpu
     A, B, Ah, Bh = synthetic.make_pair(P, COARSE, UPSAMPLE, seed=1 + rank)
     host = [t.pin_memory() for t in (A, B, Ah, Bh)]
@@ -235,6 +241,44 @@ def run_ours(args):
     ms_e2e = timed(e2e_fn, args.steps)
     clocks = sampler.stop()
 
+    def golden_errors(m):
+        """max-abs / percentile errors of m.match() on the seed-1 pair against the unmodified reference's output."""
+        import numpy as np
+        g = dict(np.load(os.path.join(ROOT, "tests", "golden", "full_sym_up.npz")))
+        ga, gb, gah, gbh = (t.to(dev) for t in synthetic.make_pair(1, COARSE, UPSAMPLE, seed=1))
+        w, c = m.match(ga, gb, im_A_high_res=gah, im_B_high_res=gbh)
+        ew = np.abs(w[:, ::8, ::8].float().cpu().numpy() - g["warp"]).max(-1)
+        ec = np.abs(c[:, ::8, ::8].float().cpu().numpy() - g["certainty"])
+        return ew, ec
+
+    parity = fast = None
+    if rank == 0:
+        ew, ec = golden_errors(model)
+        parity = {"warp": float(ew.max()), "certainty": float(ec.max()), "tol": 1e-4, "ok": bool(ew.max() <= 1e-4 and ec.max() <= 1e-4),
+                  "reference": "tests/golden/full_sym_up.npz = output of the unmodified reference (CPU fp32) for the seed-1 560->864 pair, every 8th pixel",
+                  "precision": args.precision}
+    if rank == 0 and world == 1 and args.precision == "fp32" and not args.no_fast_mode:
+        # the reference's CUDA regime (fp16 autocast) next to the parity mode: same workload, same timing method
+        import numpy as np
+        model.free_buffers()
+        model_zoo.fp32_backend = None
+        fmodel = roma_outdoor(dev, weights=mw, dinov2_weights=dw, coarse_res=COARSE, upsample_res=UPSAMPLE, amp_dtype=torch.float16)
+        main_model, model = model, fmodel
+        for _ in range(3):
+            step_device()
+        fms = timed(step_device, args.steps)
+        ew, ec = golden_errors(fmodel)
+        model = main_model
+        fast = {"precision": "fp16 operands / f32 accumulate (the reference's CUDA autocast regime)", "value": P * args.steps / (sum(fms) / 1e3),
+                "unit": "pairs/s", "ms_per_step": sum(fms) / args.steps,
+                "parity": {"warp_median": float(np.median(ew)), "warp_p99": float(np.percentile(ew, 99)), "warp_max": float(ew.max()),
+                           "certainty_median": float(np.median(ec)), "certainty_p99": float(np.percentile(ec, 99)), "certainty_max": float(ec.max()),
+                           "tol": 1e-4, "ok": bool(ew.max() <= 1e-4 and ec.max() <= 1e-4)},
+                "note": "16-bit operands cannot meet 1e-4 end to end (coarse-classifier argmax flips, SURVEY 7.2); not the headline"}
+        fmodel.free_buffers()
+        del fmodel
+    del mw, dw
+
     total_ms, total_ms_e2e = sum(ms), sum(ms_e2e)
     if world > 1:
         t = torch.tensor([total_ms, total_ms_e2e], device=dev, dtype=torch.float64)
@@ -262,12 +306,21 @@ def run_ours(args):
         if dom:
             fl, t_ms, n = by[dom]
             ach = fl / (t_ms / 1e3) / 1e12
+            # dram__bytes_read+write of one named launch of this kernel, measured by `ncu --set full` on this same command
+            # (scripts/gpu_profile.sh writes the side-car next to the ncu summary it comes from); null when not captured
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get(dom)
+            passes = 3.0 if dom == "tcgen05-split" else 1.0
             roofline = {"kernel": f"romab200_gemm[{dom}]", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"],
                         "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
-                        # dram__bytes_read+write of one representative launch (ViT fc1 3202x4096x1024 fp16, algorithmic bytes
-                        # 41.2 MB of which the 26 MB output stays in L2) from `ncu --set full`: profiles/r01_ncu_gemm_fc1.txt
-                        "traffic": 15090688 if dom == "tcgen05" else None,
-                        "traffic_launch": "vit fc1 3202x4096x1024 (profiles/r01_ncu_gemm_fc1.txt)" if dom == "tcgen05" else None,
+                        "achieved_executed": ach * passes, "frac_executed": ach * passes / peaks["bf16_sustained"],
+                        "passes": passes,
+                        "passes_note": "algorithmic FLOPs = the fp32 contraction 2MNK; the split-fp16 parity mode executes three f16 MMAs per "
+                                       "algorithmic MMA (hi.hi, hi.lo, lo.hi), so its ceiling on this axis is 1/3" if passes > 1 else None,
+                        "traffic": traffic["dram_bytes"] if traffic else None,
+                        "traffic_launch": traffic["launch"] if traffic else None,
                         "peak_source": peaks["source"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
                         "launches_timed": n, "share_of_step": t_ms / sum(ms_prof),
                         "measured_in": "second timed region of the same K steps, eager launches (per-kernel events cannot be read "
@@ -281,15 +334,17 @@ def run_ours(args):
         if cos_n:
             # executed FLOPs: the 16-bit modes run the contraction on split-fp16 operands (K' = 3K) for fp32-class accuracy;
             # the algorithmic count is the fp32 contraction the reference performs (matcher.py:191-200)
+            # (fp16 mode: K' = 3K operand trick -> flops recorded are 3x; split mode: flops recorded are algorithmic, 3 MMAs each)
             split = 3.0 if cos_backend == "tcgen05" else 1.0
+            executed = 3.0 if cos_backend == "tcgen05-split" else 1.0
             ach = cos_flops / split / (cos_ms / 1e3) / 1e12
-            pk = peaks["bf16_sustained"] if cos_backend == "tcgen05" else 72.0
-            extra.append({"kernel": f"all-pairs CosKernel (romab200_gemm, RB_EPI_COSKERNEL, {cos_backend})", "bound": "tensor" if cos_backend == "tcgen05" else "fp32",
-                          "achieved": ach, "achieved_executed": cos_flops / (cos_ms / 1e3) / 1e12, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
+            pk = peaks["bf16_sustained"] if cos_backend.startswith("tcgen05") else 72.0
+            extra.append({"kernel": f"all-pairs CosKernel (romab200_gemm, RB_EPI_COSKERNEL, {cos_backend})", "bound": "tensor" if cos_backend.startswith("tcgen05") else "fp32",
+                          "achieved": ach, "achieved_executed": cos_flops * executed / (cos_ms / 1e3) / 1e12, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
                           "launches_per_step": cos_n / args.steps, "ms_per_step": cos_ms / args.steps,
                           "note": "four 1600x1600x512 problems per pair (2.6 GFLOP each, 1.5 us at peak): size-limited, see DESIGN.md"})
         lc_fma, lc_bytes = 0.0, 0.0
-        esz = 4 if args.precision == "fp32" else 2
+        esz = 4 if args.precision.startswith("fp32") else 2
         for res, scales in ((COARSE, arch.SCALES), (UPSAMPLE, arch.UPSAMPLE_SCALES)):
             for sc in scales:
                 spec = arch.REFINERS[sc]
@@ -317,7 +372,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp16": "f16 operands / f32 accumulate (reference CUDA autocast regime)", "bf16": "bf16 operands / f32 accumulate",
-                      "fp32": "f32"}[args.precision],
+                      "fp32": "f32 (activations f32; GEMM operands as split-f16 pairs hi + 2^-11 lo on tcgen05, f32 accumulate: fp32-class)",
+                      "fp32_simt": "f32 (CUDA-core FFMA GEMMs)"}[args.precision],
             "data": "synthetic",
             "config": {"workload": "roma_outdoor 560->864, symmetric, full match()" + ("" if args.no_sample else "+sample(10000)") +
                                    " [BASELINE configs[1] per GPU]",
@@ -326,6 +382,7 @@ def run_ours(args):
                        "l2": "256 MiB buffer written between timed steps; per-step activations also exceed the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_box[0],
                     "ms_per_step": total_ms_e2e / args.steps},
+            "parity": parity, "fast_mode": fast,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_kernels": extra, "cpu_baseline": cpu,
             "stage_ms_per_step": {k: round(v, 3) for k, v in sorted(stages.items(), key=lambda kv: -kv[1])},
             "gemm_backends": {k: {"tflops": v[0] / (v[1] / 1e3) / 1e12, "ms_per_step": v[1] / args.steps, "launches_per_step": v[2] / args.steps}
@@ -346,7 +403,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("ROMA_B200_PRECISION", "fp16"), choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("ROMA_B200_PRECISION", "fp32"), choices=["fp32", "fp32_simt", "fp16", "bf16"])
+    ap.add_argument("--no-fast-mode", action="store_true", help="skip the fp16 fast-mode leg reported beside the parity mode")
     ap.add_argument("--pairs-per-gpu", type=int, default=1)
     ap.add_argument("--no-sample", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
