@@ -110,6 +110,8 @@ int romab200_softmax_rows(const rb_softmax_args* args, void* stream);
  * out[b, i, h*d:(h+1)*d] = softmax_j(q_i . k_j / sqrt(d)) v_j.  head_dim 64 or 128. */
 typedef struct {
     const void* qkv; void* out; int64_t ld_qkv, ld_out; int32_t batch, n_tokens, heads, head_dim, dtype;
+    /* dtype == RB_F16S (head_dim 64): qkv and out are split-fp16 pairs, these are their second planes; fp32-class result */
+    const void* qkv_lo; void* out_lo;
 } rb_flash_attn_args;
 int romab200_flash_attn(const rb_flash_attn_args* args, void* stream);
 

@@ -317,6 +317,246 @@ __global__ void __launch_bounds__(192, 1) flash_attn_kernel(const __grid_constan
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
+
+// ================================================================================================================
+// Split-fp16 (RB_F16S) variant for the parity mode, head_dim 64 (DINOv2 ViT-L): fp32-class attention on the f16 tensor pipe.
+//   q, k, v arrive as (hi, lo') plane pairs (value = hi + lo' * 2^-11, written by the qkv GEMM epilogue).
+//   S_j = Q K_j^T with three MMAs per k-step into TWO accumulators (main: hi.hi; cross: hi.lo' + lo'.hi), score = main +
+//         cross * 2^-11; key tiles of 64 so that two score stages (2 x 128 columns) + O fit the 512 TMEM columns.
+//   P V : the probabilities are written in an exponent-shifted form so that ONE accumulator suffices:
+//         O' = sum_j (Pt_hi + Pt_lo) V_hi + P_hi V_lo'      with Pt = 2048 p, Pt_hi = fp16(Pt), Pt_lo = fp16(Pt - Pt_hi),
+//         P_hi = fp16(p) = Pt_hi / 2048, i.e. O' = 2048 * sum p (V_hi + V_lo' / 2048) up to a 2^-22 relative term.  p <= 1, so
+//         Pt <= 2048 never overflows; the unscaled low part Pt_lo only underflows for p < 6e-5, where its absolute error
+//         (1.5e-11 in units of p) is irrelevant.
+//   out  = O' / (2048 l) written as an RB_F16S pair for the projection GEMM.
+// Warp roles and barriers are those of flash_attn_kernel above.
+// ================================================================================================================
+struct FaSplitParams {
+    void* out_hi; void* out_lo; int64_t ldo;
+    int N, heads, dim;
+    float scale_log2;
+};
+
+struct FaSplitCfg {
+    static constexpr int D = 64, BQ = 128, BKV = 64, STAGES = 3;
+    static constexpr int Q_BYTES = BQ * D * 2;              // one plane
+    static constexpr int KV_BYTES = BKV * D * 2;            // one plane of one of K, V
+    static constexpr int STAGE_BYTES = 4 * KV_BYTES;        // K_hi, K_lo, V_hi, V_lo
+    static constexpr int P_BYTES = BQ * BKV * 2;            // one of the three probability operands
+    static constexpr int SMEM = 2 * Q_BYTES + STAGES * STAGE_BYTES + 3 * P_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = 512;                   // S: 2 stages x (64 main + 64 cross), O: 64  (power of two >= 320)
+};
+
+__global__ void __launch_bounds__(192, 1) flash_attn_split_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                                                                   const FaSplitParams p) {
+    rb::pdl_wait();
+    using namespace fa;
+    using Cfg = FaSplitCfg;
+    constexpr int STAGES = Cfg::STAGES, BQ = Cfg::BQ, BKV = Cfg::BKV, D = Cfg::D;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQh = smem;
+    uint8_t* sQl = sQh + Cfg::Q_BYTES;
+    uint8_t* sKV = sQl + Cfg::Q_BYTES;                        // per stage: K_hi | K_lo | V_hi | V_lo
+    uint8_t* sP = sKV + STAGES * Cfg::STAGE_BYTES;            // Pt_hi | Pt_lo | P_hi
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 3 * Cfg::P_BYTES);
+    uint64_t* q_full = bars;                  // [1]
+    uint64_t* kv_full = bars + 1;             // [STAGES]
+    uint64_t* kv_empty = kv_full + STAGES;    // [STAGES]
+    uint64_t* s_full = kv_empty + STAGES;     // [2]
+    uint64_t* s_empty = s_full + 2;           // [2]
+    uint64_t* p_ready = s_empty + 2;          // [1]
+    uint64_t* pv_done = p_ready + 1;          // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BQ, head = blockIdx.y, img = blockIdx.z;
+    const int ntiles = (p.N + BKV - 1) / BKV;
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
+        mbar_init(p_ready, 4);
+        mbar_init(pv_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base;              // stage s: main at s * 128, cross at s * 128 + 64
+    const uint32_t tmem_O = tmem_base + 256;        // columns [256, 320)
+
+    if (warp == 0) {
+        // ===== TMA producer (boxes of 64 rows x 64 columns; the 128-query tile is two boxes per plane) =====
+        if (lane == 0) {
+            const int cq = head * D, ck = p.dim + head * D, cv = 2 * p.dim + head * D;
+            mbar_expect_tx(q_full, 2 * Cfg::Q_BYTES);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                tma_load_3d(sQh + h * (64 * 128), &map_hi, q_full, cq, q0 + 64 * h, img);
+                tma_load_3d(sQl + h * (64 * 128), &map_lo, q_full, cq, q0 + 64 * h, img);
+            }
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % STAGES;
+                const uint32_t u = j / STAGES;
+                mbar_wait(&kv_empty[s], (u & 1) ^ 1);
+                mbar_expect_tx(&kv_full[s], Cfg::STAGE_BYTES);
+                uint8_t* st = sKV + s * Cfg::STAGE_BYTES;
+                tma_load_3d(st, &map_hi, &kv_full[s], ck, j * BKV, img);
+                tma_load_3d(st + Cfg::KV_BYTES, &map_lo, &kv_full[s], ck, j * BKV, img);
+                tma_load_3d(st + 2 * Cfg::KV_BYTES, &map_hi, &kv_full[s], cv, j * BKV, img);
+                tma_load_3d(st + 3 * Cfg::KV_BYTES, &map_lo, &kv_full[s], cv, j * BKV, img);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // S = Q K^T : A, B K-major fp16, N = 64;   O' += P V : A K-major, B MN-major, N = 64
+            const uint32_t idesc_s = (1u << 4) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+            const uint32_t idesc_o = (1u << 4) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+            const uint32_t qh_addr = smem_u32(sQh), ql_addr = smem_u32(sQl), p_addr = smem_u32(sP);
+            auto issue_s = [&](int j) {
+                const int s = j % STAGES;
+                mbar_wait(&kv_full[s], (j / STAGES) & 1);
+                const uint32_t u = j >> 1;                       // previous uses of this score stage
+                mbar_wait(&s_empty[j & 1], (u & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t kh_addr = smem_u32(sKV + s * Cfg::STAGE_BYTES), kl_addr = kh_addr + Cfg::KV_BYTES;
+                const uint32_t t_main = tmem_S + (j & 1) * 128, t_cross = t_main + 64;
+#pragma unroll
+                for (int k = 0; k < D / 16; ++k) {
+                    const uint32_t off = k * 32;                 // 32 B per K step inside the 128-byte swizzle atom
+                    const uint64_t qh = smem_desc(qh_addr + off, 16, 1024), ql = smem_desc(ql_addr + off, 16, 1024);
+                    const uint64_t kh = smem_desc(kh_addr + off, 16, 1024), kl = smem_desc(kl_addr + off, 16, 1024);
+                    umma_f16(t_main, qh, kh, idesc_s, k != 0);
+                    umma_f16(t_cross, qh, kl, idesc_s, k != 0);
+                    umma_f16(t_cross, ql, kh, idesc_s, 1u);
+                }
+                umma_commit(&s_full[j & 1]);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < ntiles; ++j) {
+                if (j + 1 < ntiles) issue_s(j + 1);
+                mbar_wait(p_ready, j & 1);
+                tc_fence_after();
+                const int s = j % STAGES;
+                const uint32_t vh_addr = smem_u32(sKV + s * Cfg::STAGE_BYTES + 2 * Cfg::KV_BYTES), vl_addr = vh_addr + Cfg::KV_BYTES;
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    // P operands: 128 rows x 64 keys (one swizzle atom wide), 16 keys = 32 B; V tile [64 keys x 128 B]: 16 keys = 2048 B
+                    const uint64_t pth = smem_desc(p_addr + k * 32, 16, 1024), ptl = smem_desc(p_addr + Cfg::P_BYTES + k * 32, 16, 1024);
+                    const uint64_t ph = smem_desc(p_addr + 2 * Cfg::P_BYTES + k * 32, 16, 1024);
+                    const uint64_t vh = smem_desc(vh_addr + k * 2048, BKV * 128, 1024), vl = smem_desc(vl_addr + k * 2048, BKV * 128, 1024);
+                    umma_f16(tmem_O, pth, vh, idesc_o, (j | k) != 0);
+                    umma_f16(tmem_O, ptl, vh, idesc_o, 1u);
+                    umma_f16(tmem_O, ph, vl, idesc_o, 1u);
+                }
+                umma_commit(&kv_empty[s]);
+                umma_commit(pv_done);
+            }
+        }
+    } else {
+        // ===== softmax / correction / epilogue: one thread per query row =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < ntiles; ++j) {
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            float sc[64];
+            {
+                float cr[32];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    tmem_ld32(tmem_S + lane_addr + (j & 1) * 128 + c * 32, sc + c * 32);
+                    tmem_ld32(tmem_S + lane_addr + (j & 1) * 128 + 64 + c * 32, cr);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) sc[c * 32 + i] = fmaf(cr[i], 1.0f / 2048.0f, sc[c * 32 + i]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[j & 1]);
+            const int valid = min(BKV, p.N - j * BKV);
+            float m_new = m_run;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                sc[i] = i < valid ? sc[i] * p.scale_log2 : -INFINITY;
+                m_new = fmaxf(m_new, sc[i]);
+            }
+            const float alpha = ex2(m_run - m_new);           // 0 on the first tile (m_run = -inf)
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);              // PV_{j-1} retired: O is stable, the P buffers are free
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, m_new > m_run)) {
+#pragma unroll
+                    for (int c = 0; c < D / 32; ++c) {
+                        float o[32];
+                        tmem_ld32(tmem_O + lane_addr + c * 32, o);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] *= alpha;
+                        tmem_st32(tmem_O + lane_addr + c * 32, o);
+                    }
+                }
+            }
+            float lsum = 0.f;
+            // P rows -> K-major SW128 (one 64-key atom): 16-byte chunk c' = (key / 8) XOR (row % 8)
+            uint8_t* prow = sP + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                __half pth[8], ptl[8], ph[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float pv = ex2(sc[c * 8 + e] - m_new);
+                    lsum += pv;
+                    const float pt = pv * 2048.0f;
+                    pth[e] = __float2half_rn(pt);
+                    ptl[e] = __float2half_rn(pt - __half2float(pth[e]));
+                    ph[e] = __float2half_rn(pv);
+                }
+                const int cc = c ^ (row & 7);
+                *reinterpret_cast<uint4*>(prow + cc * 16) = *reinterpret_cast<uint4*>(pth);
+                *reinterpret_cast<uint4*>(prow + Cfg::P_BYTES + cc * 16) = *reinterpret_cast<uint4*>(ptl);
+                *reinterpret_cast<uint4*>(prow + 2 * Cfg::P_BYTES + cc * 16) = *reinterpret_cast<uint4*>(ph);
+            }
+            l_run = l_run * alpha + lsum;
+            m_run = m_new;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to UMMA
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_ready);
+        }
+        mbar_wait(pv_done, (ntiles - 1) & 1);
+        tc_fence_after();
+        const int qi = q0 + row;
+        const float inv = 1.0f / (l_run * 2048.0f);
+        const int64_t o_off = ((int64_t)img * p.N + qi) * p.ldo + head * D;
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+            float o[32];
+            tmem_ld32(tmem_O + lane_addr + c * 32, o);
+            if (qi < p.N) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    __half hi[8], lo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) split_f16s(o[g * 8 + e] * inv, hi[e], lo[e]);
+                    *reinterpret_cast<uint4*>((__half*)p.out_hi + o_off + c * 32 + g * 8) = *reinterpret_cast<uint4*>(hi);
+                    *reinterpret_cast<uint4*>((__half*)p.out_lo + o_off + c * 32 + g * 8) = *reinterpret_cast<uint4*>(lo);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
 typedef CUresult (*EncodeTiledFnFa)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -324,11 +564,12 @@ typedef CUresult (*EncodeTiledFnFa)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 template <int D, typename T>
 static int launch_fa(const CUtensorMap& map, const FaParams& p, int batch, cudaStream_t st) {
     using Cfg = FaCfg<D>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};      // function attributes are per device
+    const int dev = current_device() & 63;
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<D, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         RB_REQUIRE(e == cudaSuccess, "flash_attn: cannot set %d bytes of dynamic shared memory: %s", Cfg::SMEM, cudaGetErrorString(e));
-        configured = true;
+        configured[dev] = true;
     }
     dim3 grid((p.N + Cfg::BQ - 1) / Cfg::BQ, p.heads, batch);
     rb::launch_pdl(flash_attn_kernel<D, T>, dim3(grid), dim3(192), Cfg::SMEM, st, map, p);
@@ -341,8 +582,10 @@ using namespace rb;
 
 extern "C" int romab200_flash_attn(const rb_flash_attn_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    RB_REQUIRE(a->dtype == RB_F16 || a->dtype == RB_BF16, "flash_attn: 16-bit inputs only (fp32 attention uses the GEMM path)");
-    RB_REQUIRE(a->head_dim == 64 || a->head_dim == 128, "flash_attn: head_dim %d unsupported (64, 128)", a->head_dim);
+    RB_REQUIRE(a->dtype == RB_F16 || a->dtype == RB_BF16 || a->dtype == RB_F16S, "flash_attn: 16-bit or split-fp16 inputs only");
+    RB_REQUIRE(a->head_dim == 64 || (a->head_dim == 128 && a->dtype != RB_F16S), "flash_attn: head_dim %d unsupported (64, 128; split-fp16: 64)", a->head_dim);
+    RB_REQUIRE(a->dtype != RB_F16S || (a->qkv_lo && a->out_lo && ((uintptr_t)a->qkv_lo) % 16 == 0 && ((uintptr_t)a->out_lo) % 16 == 0),
+               "flash_attn: split-fp16 needs 16-byte aligned qkv_lo and out_lo planes");
     const int dim = a->heads * a->head_dim;
     RB_REQUIRE(a->ld_qkv >= 3 * dim && (a->ld_qkv * 2) % 16 == 0 && ((uintptr_t)a->qkv) % 16 == 0, "flash_attn: qkv pitch/alignment");
     RB_REQUIRE(a->ld_out >= dim && (a->ld_out * 2) % 16 == 0 && ((uintptr_t)a->out) % 16 == 0, "flash_attn: out pitch/alignment");
@@ -364,6 +607,29 @@ extern "C" int romab200_flash_attn(const rb_flash_attn_args* a, void* stream) {
                      dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RB_REQUIRE(r == CUDA_SUCCESS, "flash_attn: cuTensorMapEncodeTiled failed with %d", (int)r);
+    if (a->dtype == RB_F16S) {
+        CUtensorMap map_hi, map_lo;
+        cuuint32_t box64[3] = {64, 64, 1};
+        r = enc(&map_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(a->qkv), dims, strides, box64, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RB_REQUIRE(r == CUDA_SUCCESS, "flash_attn: cuTensorMapEncodeTiled (hi plane) failed with %d", (int)r);
+        r = enc(&map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(a->qkv_lo), dims, strides, box64, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RB_REQUIRE(r == CUDA_SUCCESS, "flash_attn: cuTensorMapEncodeTiled (lo plane) failed with %d", (int)r);
+        static bool configured[64] = {};
+        const int dev = current_device() & 63;
+        if (!configured[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(flash_attn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FaSplitCfg::SMEM);
+            RB_REQUIRE(e == cudaSuccess, "flash_attn: cannot set %d bytes of dynamic shared memory: %s", FaSplitCfg::SMEM, cudaGetErrorString(e));
+            configured[dev] = true;
+        }
+        FaSplitParams sp;
+        sp.out_hi = a->out; sp.out_lo = a->out_lo; sp.ldo = a->ld_out; sp.N = a->n_tokens; sp.heads = a->heads; sp.dim = dim;
+        sp.scale_log2 = 1.4426950408889634f / sqrtf((float)a->head_dim);
+        dim3 grid((a->n_tokens + FaSplitCfg::BQ - 1) / FaSplitCfg::BQ, a->heads, a->batch);
+        rb::launch_pdl(flash_attn_split_kernel, dim3(grid), dim3(192), FaSplitCfg::SMEM, st, map_hi, map_lo, sp);
+        return check_launch("flash_attn_split");
+    }
     FaParams p;
     p.out = a->out; p.ldo = a->ld_out; p.N = a->n_tokens; p.heads = a->heads; p.dim = dim; p.is_bf16 = a->dtype == RB_BF16;
     p.scale_log2 = 1.4426950408889634f / sqrtf((float)a->head_dim);

@@ -478,6 +478,107 @@ __global__ void __launch_bounds__(256) refiner_block_small_kernel(const T* __res
     for (int v = 0; v < C / 8; ++v) *reinterpret_cast<uint4*>(op + 8 * v) = *reinterpret_cast<const uint4*>(&res[8 * v]);
 }
 
+
+// The same block for fp32 maps (parity mode): fp32 tile in shared memory, fp32 FFMA throughout, fp32 result — the arithmetic of
+// the un-fused fp32 path (depthwise kernel + fp32 pointwise GEMM) in one pass over the activation.  Dynamic shared memory:
+// input tile 20 rows x 504 words (pixel stride 24, row stride = 24 mod 32 words so that the 64-bit (channel pair, row) reads of a
+// half-warp fall into 32 distinct banks) + the 16x16x25 intermediate.
+template <int C>
+struct SmallF32Cfg {
+    static constexpr int TS = 16, IN = TS + 4, PS = C, RS = IN * PS + 24, MS = C + 1;
+    static constexpr int SMEM = (IN * RS + TS * TS * MS) * 4;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) refiner_block_small_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t ld,
+                                                                      const float* __restrict__ dw_w, int64_t ldw, const float* __restrict__ dw_b,
+                                                                      const __grid_constant__ SmallPw<C> pw, int H, int W, int tiles_x) {
+    rb::pdl_wait();
+    using Cfg = SmallF32Cfg<C>;
+    constexpr int TS = Cfg::TS, IN = Cfg::IN, CP = C / 2, PS = Cfg::PS, RS = Cfg::RS, MS = Cfg::MS;
+    extern __shared__ __align__(16) float sm_small[];
+    float* tile = sm_small;                   // [IN][RS]
+    float* mid = sm_small + IN * RS;          // [TS*TS][MS]
+    const int tid = threadIdx.x;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, b = blockIdx.y;
+    const int x0 = tx * TS, y0 = ty * TS;
+    const float* inb = in + (int64_t)b * H * W * ld;
+    {   // 16-byte global loads, all issued before the first shared store
+        constexpr int VPP = C / 4, NV = IN * IN * VPP, PER = (NV + 255) / 256;
+        float4 vals[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = tid + k * 256;
+            const int pix = i / VPP, v = i - pix * VPP;
+            const int py = pix / IN, px = pix - py * IN;
+            const int yy = y0 + py - 2, xx = x0 + px - 2;
+            vals[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < NV && yy >= 0 && yy < H && xx >= 0 && xx < W)
+                vals[k] = *reinterpret_cast<const float4*>(inb + ((int64_t)yy * W + xx) * ld + 4 * v);
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = tid + k * 256;
+            if (i < NV) {
+                const int pix = i / VPP, v = i - pix * VPP;
+                const int py = pix / IN, px = pix - py * IN;
+                *reinterpret_cast<float4*>(&tile[py * RS + px * PS + 4 * v]) = vals[k];      // RS, PS multiples of 4: 16-byte aligned
+            }
+        }
+    }
+    // ---- depthwise: thread = (channel pair, output row); taps in registers, packed FFMA2
+    const int cp = tid % CP, row = tid / CP;
+    float2 wv[25];
+    float2 bv = make_float2(0.f, 0.f);
+    if (row < TS) {
+#pragma unroll
+        for (int t = 0; t < 25; ++t) wv[t] = make_float2(dw_w[(int64_t)t * ldw + 2 * cp], dw_w[(int64_t)t * ldw + 2 * cp + 1]);
+        bv = make_float2(dw_b[2 * cp], dw_b[2 * cp + 1]);
+    }
+    __syncthreads();
+    if (row < TS) {
+        float2 acc[TS];
+#pragma unroll
+        for (int i = 0; i < TS; ++i) acc[i] = bv;
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+            for (int px = 0; px < IN; ++px) {
+                const float2 v = *reinterpret_cast<const float2*>(&tile[(row + ky) * RS + px * PS + 2 * cp]);
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                    const int ox = px - kx;
+                    if (ox >= 0 && ox < TS) acc[ox] = __ffma2_rn(wv[ky * 5 + kx], v, acc[ox]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TS; ++i) {
+            mid[(row * TS + i) * MS + 2 * cp] = fmaxf(acc[i].x, 0.f);
+            mid[(row * TS + i) * MS + 2 * cp + 1] = fmaxf(acc[i].y, 0.f);
+        }
+    }
+    __syncthreads();
+    // ---- pointwise: thread = pixel; weights are constant-bank operands of the FFMAs
+    const int py = tid / TS, px = tid - py * TS;
+    const int yy = y0 + py, xx = x0 + px;
+    if (yy >= H || xx >= W) return;
+    float av[C];
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) av[ci] = mid[tid * MS + ci];
+    float res[C];
+#pragma unroll
+    for (int co = 0; co < C; ++co) {
+        float o = pw.b[co];
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) o = fmaf(pw.w[co][ci], av[ci], o);
+        res[co] = o;
+    }
+    float* op = out + ((int64_t)b * H * W + (int64_t)yy * W + xx) * ld;
+#pragma unroll
+    for (int v = 0; v < C / 4; ++v) *reinterpret_cast<float4*>(op + 4 * v) = make_float4(res[4 * v], res[4 * v + 1], res[4 * v + 2], res[4 * v + 3]);
+}
+
 // --------------------------------------------------------------------------------------------------
 // out_conv (C -> 3, fp32) + state update: one warp per pixel
 // --------------------------------------------------------------------------------------------------
@@ -725,6 +826,10 @@ extern "C" int romab200_dwconv5x5_relu(const rb_dwconv_args* a, void* stream) {
         ((uintptr_t)a->in) % 16 == 0 && ((uintptr_t)a->out) % 4 == 0) {
         return dwconv_tma(a, st);
     }
+    if (a->dtype == RB_F32 && a->out_lo && a->ldi % 4 == 0 && a->ldo % 2 == 0 && a->ldi >= cpad && a->ldo >= cpad &&
+        ((uintptr_t)a->in) % 16 == 0 && ((uintptr_t)a->out) % 4 == 0 && ((uintptr_t)a->out_lo) % 4 == 0) {
+        return dwconv_tma(a, st);           // parity mode: fp32 map -> RB_F16S pair, TMA-fed persistent kernel
+    }
     RB_REQUIRE(!a->out_lo || a->dtype == RB_F32, "dwconv: the RB_F16S output (out_lo) is for fp32 maps");
     if (a->dtype == RB_F32 && a->out_lo) rb::launch_pdl(dwconv5x5_relu_kernel<float, true>, dim3(grid), dim3(256), 0, st, (const float*)a->in, (float*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x, (__half*)a->out_lo);
     else if (a->dtype == RB_F32) rb::launch_pdl(dwconv5x5_relu_kernel<float, false>, dim3(grid), dim3(256), 0, st, (const float*)a->in, (float*)a->out, a->ldi, a->ldo, a->weight, a->ldw, a->bias, a->h, a->w, a->c, tiles_x, (__half*)nullptr);
@@ -736,8 +841,8 @@ extern "C" int romab200_dwconv5x5_relu(const rb_dwconv_args* a, void* stream) {
 extern "C" int romab200_refiner_block_small(const rb_refiner_block_small_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->c == 24, "refiner_block_small: only C = 24 is instantiated (got %d)", a->c);
-    RB_REQUIRE(a->dtype == RB_F16 || a->dtype == RB_BF16, "refiner_block_small: 16-bit activations only");
-    RB_REQUIRE(a->ld % 8 == 0 && ((uintptr_t)a->in) % 16 == 0 && ((uintptr_t)a->out) % 16 == 0 && a->in != a->out, "refiner_block_small: bad layout");
+    RB_REQUIRE(a->dtype == RB_F16 || a->dtype == RB_BF16 || a->dtype == RB_F32, "refiner_block_small: fp16 / bf16 / fp32 activations");
+    RB_REQUIRE(a->ld % (a->dtype == RB_F32 ? 4 : 8) == 0 && ((uintptr_t)a->in) % 16 == 0 && ((uintptr_t)a->out) % 16 == 0 && a->in != a->out, "refiner_block_small: bad layout");
     int tiles_x = (a->w + 15) / 16, tiles_y = (a->h + 15) / 16;
     dim3 grid(tiles_x * tiles_y, a->batch);
     RB_REQUIRE(grid.y <= 65535, "refiner_block_small: batch too large");
@@ -747,7 +852,17 @@ extern "C" int romab200_refiner_block_small(const rb_refiner_block_small_args* a
         for (int ci = 0; ci < 24; ++ci) pw.w[co][ci] = a->pw_weight_host[co * 24 + ci];
         pw.b[co] = a->pw_bias_host[co];
     }
-    if (a->dtype == RB_F16)
+    if (a->dtype == RB_F32) {
+        static bool cfg[64] = {};            // function attributes are per device
+        const int dev = current_device() & 63;
+        if (!cfg[dev]) {
+            RB_REQUIRE(cudaFuncSetAttribute(refiner_block_small_f32_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallF32Cfg<24>::SMEM) == cudaSuccess,
+                       "refiner_block_small: smem attribute");
+            cfg[dev] = true;
+        }
+        rb::launch_pdl(refiner_block_small_f32_kernel<24>, dim3(grid), dim3(256), SmallF32Cfg<24>::SMEM, st, (const float*)a->in, (float*)a->out, a->ld, a->dw_weight, a->ldw,
+                       a->dw_bias, pw, a->h, a->w, tiles_x);
+    } else if (a->dtype == RB_F16)
         rb::launch_pdl(refiner_block_small_kernel<__half, 24>, dim3(grid), dim3(256), 0, st, (const __half*)a->in, (__half*)a->out, a->ld, a->dw_weight, a->ldw, a->dw_bias,
                        pw, a->h, a->w, tiles_x);
     else

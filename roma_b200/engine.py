@@ -65,6 +65,7 @@ class Engine:
         self.overlap_cnn = True                  # VGG/proj branch on a side stream, overlapping ViT / GP / decoder
         self.gp_tensor_core = True               # all-pairs CosKernel on tcgen05 (split-fp16 operands) in the 16-bit modes
         self.fused_c144 = True                   # stride-2 refiner blocks as one fused DW + tcgen05-PW kernel
+        self.fused_small_f32 = True              # fp32 modes: stride-1 (C = 24) refiner blocks as one fused fp32 CUDA-core kernel
         self._side = None
         self.profile: Optional[dict] = None      # set to {} to collect CUDA-event timings per stage (bench.py)
         self.gemm_profile: Optional[list] = None  # set to [] to time every GEMM launch: (backend, flops, start, end, shape, epilogue)
@@ -248,6 +249,12 @@ class Engine:
             return
         npad = pad8(N)
         ld = 3 * dim
+        if self.split and d == 64 and self.use_flash_attn:
+            # parity mode, ViT heads: fused split-fp16 attention (three MMAs per k-step for QK^T and for PV), no score traffic
+            with self.stage(f"  attn.{tag}"):
+                call("romab200_flash_attn", "rb_flash_attn_args", qkv=qkv.hi, qkv_lo=qkv.lo, out=out.hi, out_lo=out.lo, ld_qkv=ld, ld_out=dim,
+                     batch=Bn, n_tokens=N, heads=heads, head_dim=d, dtype=F16S)
+            return
         if self.split:
             # parity mode: q, k, v, the probabilities and the result are RB_F16S pairs; scores are fp32.  The 1/sqrt(d) scale
             # rides on the QK^T epilogue like below.
@@ -479,8 +486,11 @@ class Engine:
         if self.debug is not None:
             self.debug[f"{tag}.refiner_in"] = d.view(D, h, w, cp)[..., :c].float().clone()
         rows = D * h * w
-        if c == 24 and self.dtype != torch.float32:
+        if c == 24 and (self.dtype != torch.float32 or self.fused_small_f32):
             # thin stride-1 maps: one fused DW5x5+ReLU+PW kernel per block, ping-ponging between the two buffers
+            # (fp32 maps: fp32 FFMA throughout, the arithmetic of the un-fused fp32 path)
+            if t is None:
+                t = self.buf(f"ref.t.{tag}", (D * h * w, cp), zero=True)
             for blk in R["blocks"]:
                 call("romab200_refiner_block_small", "rb_refiner_block_small_args", **{"in": d}, out=t, ld=cp, dw_weight=blk["dw_w"],
                      ldw=cp, dw_bias=blk["dw_b"], pw_weight_host=blk["pw_w_host"].data_ptr(), pw_bias_host=blk["pw_b_host"].data_ptr(), batch=D, h=h, w=w, c=c, dtype=self.dt)

@@ -178,7 +178,7 @@ class PackedWeights:
                 pw_b=_vec(sd[f"{q}.3.bias"], self.device),
                 # thin maps (C = 24) run the fused CUDA-core block: fp32 copy of the compute-dtype-rounded weights
                 # thin maps: the fused block kernel takes its pointwise weights as launch parameters, i.e. from host memory
-                pw_w_host=pw.to(self.dtype).float().contiguous().cpu() if c <= 32 else None,
+                pw_w_host=pw.to(self.dtype).float().contiguous().cpu() if c <= 32 else None,      # (fp32 modes: exact)
                 pw_b_host=sd[f"{q}.3.bias"].float().contiguous().cpu() if c <= 32 else None,
             ))
         ow = torch.zeros(3, cp)

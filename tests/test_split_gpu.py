@@ -146,6 +146,25 @@ def test_split_attention_chain(d, N):
     assert rel_err(O.join(), ref_o) < 3e-6
 
 
+@pytest.mark.parametrize("N,scale", [(203, 0.7), (1601, 0.7), (128, 3.0), (64, 0.05), (1, 1.0)])
+def test_split_flash_attention(N, scale):
+    """Fused split-fp16 attention (head_dim 64) against float64 SDPA: fp32-class, incl. ragged last key tile, peaked
+    (scale 3) and flat (scale 0.05) score distributions."""
+    Bn, H, d = 2, 3, 64
+    dim = H * d
+    qkv32 = rnd(Bn * N, 3 * dim, seed=1, scale=scale)
+    qkv = dev_split(qkv32, Bn * N, 3 * dim, 3 * dim)
+    O = Split(torch.full((Bn * N, dim), 9.0, dtype=torch.float16, device=DEV), torch.full((Bn * N, dim), 9.0, dtype=torch.float16, device=DEV))
+    call("romab200_flash_attn", "rb_flash_attn_args", qkv=qkv.hi, qkv_lo=qkv.lo, out=O.hi, out_lo=O.lo, ld_qkv=3 * dim, ld_out=dim,
+         batch=Bn, n_tokens=N, heads=H, head_dim=d, dtype=F16S)
+    q, k, v = qkv32.double().reshape(Bn, N, 3, H, d).unbind(2)
+    ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2).reshape(Bn * N, dim)
+    f32 = F.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2)).transpose(1, 2).reshape(Bn * N, dim)
+    e_split, e_f32 = rel_err(O.join(), ref), rel_err(f32, ref)
+    print(f"flash split N={N}: rel err {e_split:.2e} (torch fp32 SDPA: {e_f32:.2e})")
+    assert e_split <= max(4 * e_f32, 2e-6), (e_split, e_f32)
+
+
 @pytest.mark.parametrize("cin,cout,H,W", [(64, 64, 20, 36), (128, 256, 9, 13)])
 def test_split_conv3x3_taps_maxpool(cin, cout, H, W):
     """VGG layer in the parity mode: 9-tap GEMM on a zero-padded RB_F16S map -> RB_F16S map, then the pair-wise max-pool."""
@@ -227,3 +246,39 @@ def test_split_coskernel_matrix():
     Kp = Split(torch.zeros(n, n, dtype=torch.float16, device=DEV), torch.zeros(n, n, dtype=torch.float16, device=DEV))
     sgemm(xs, ys, Kp, n, n, c, c, c, n, epi=cabi.EPI_COSKERNEL, norm_a=nx, norm_b=ny, eps=1e-6, inv_t=5.0, diag_add=0.0, cos_normalized=1)
     assert (Kp.join().double() - (ref - 0.1 * torch.eye(n, device=DEV, dtype=torch.float64))).abs().max() < 5e-6
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 37, 50), (1, 16, 16), (2, 5, 3)])
+def test_refiner_block_small_fp32(B, H, W):
+    """Fused thin-map block (DW5x5 + ReLU + PW, C = 24) on fp32 maps: fp32 FFMA throughout, against conv2d in float64."""
+    C = 24
+    x = rnd(B, C, H, W, seed=1)
+    dw, db = rnd(C, 1, 5, 5, seed=2, scale=0.3), rnd(C, seed=3)
+    pw, pb = rnd(C, C, seed=4, scale=0.3), rnd(C, seed=5)
+    mid = F.relu(F.conv2d(x.double(), dw.double(), db.double(), padding=2, groups=C))
+    ref = (torch.einsum("bchw,oc->bohw", mid, pw.double()) + pb.double()[None, :, None, None]).permute(0, 2, 3, 1)
+    xi = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.zeros(B, H, W, C, device=DEV)
+    dwt = dw.reshape(C, 25).t().contiguous()
+    pw_host, pb_host = pw.cpu().contiguous(), pb.cpu().contiguous()       # host arrays: they travel as kernel parameters
+    call("romab200_refiner_block_small", "rb_refiner_block_small_args", **{"in": xi}, out=out, ld=C, dw_weight=dwt, ldw=C, dw_bias=db,
+         pw_weight_host=pw_host.data_ptr(), pw_bias_host=pb_host.data_ptr(), batch=B, h=H, w=W, c=C, dtype=F32)
+    assert rel_err(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 150, 19, 37), (1, 64, 8, 16), (2, 569, 54, 54), (1, 70, 5, 3), (2, 24, 33, 20), (1, 144, 40, 48)])
+def test_dwconv_fp32_tma_split_out(B, C, H, W):
+    """TMA-fed depthwise 5x5 + ReLU on fp32 maps with the RB_F16S result (ragged 16x16 tiles, channel tail, zero-filled
+    borders) against conv2d in float64."""
+    x = rnd(B, C, H, W, seed=1)
+    w, b = rnd(C, 1, 5, 5, seed=2, scale=0.3), rnd(C, seed=3)
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=2, groups=C)).permute(0, 2, 3, 1)
+    ld = (C + 7) // 8 * 8
+    xi = torch.zeros(B, H, W, ld, device=DEV)
+    xi[..., :C] = x.permute(0, 2, 3, 1)
+    wt = torch.zeros(25, ld, device=DEV)
+    wt[:, :C] = w.reshape(C, 25).t()
+    t = Split(torch.full((B, H, W, ld), 7.0, dtype=torch.float16, device=DEV), torch.full((B, H, W, ld), 7.0, dtype=torch.float16, device=DEV))
+    call("romab200_dwconv5x5_relu", "rb_dwconv_args", **{"in": xi}, out=t.hi, out_lo=t.lo, ldi=ld, ldo=ld, weight=wt, ldw=ld, bias=b,
+         batch=B, h=H, w=W, c=C, dtype=F32)
+    assert rel_err(t.join()[..., :C], ref) < 2e-6
