@@ -155,6 +155,169 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Epilogue of one 128 x BN accumulator tile by the EPI_WARPS epilogue warps of a CTA (shared by the 1-CTA and the 2-CTA
+// kernels): stage the per-column vectors, wait for the accumulator, tcgen05.ld, fused epilogue, 16-byte stores.
+// `tmem_acc` = TMEM address of the tile's main accumulator (lane 0); the cross accumulator of the SPLIT variant sits BN columns
+// further.  (m0, n0) = first row / column of the tile, z0 / z1 = batch indices.
+template <int BN, bool SPLIT, int EPI_WARPS>
+__device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, uint64_t* full_bar, uint32_t full_parity, int m0, int n0,
+                                                 int z0, int z1, int q, int half, int lane, int et, float* s_vec0, float* s_vec1) {
+    Epilogue e = p.epi;
+    e.C = (char*)e.C + (z0 * p.sc0 + z1 * p.sc1) * dtype_size(e.dtype_c);
+    if (e.C_lo) e.C_lo = (char*)e.C_lo + (z0 * p.sc0 + z1 * p.sc1) * 2;
+    if (e.R) e.R = (const char*)e.R + (z0 * p.sr0 + z1 * p.sr1) * dtype_size(e.dtype_r);
+    if (e.norm_a) e.norm_a += z0 * p.sna0;
+    if (e.norm_b) e.norm_b += z0 * p.snb0;
+    // stage the per-column epilogue vectors of this tile in shared memory (read back as broadcast float4s)
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // everyone is done with the previous tile's vectors
+    for (int t = et; t < BN; t += 32 * EPI_WARPS) {
+        const int n = n0 + t;
+        const float* v0 = e.epi == RB_EPI_COSKERNEL ? e.norm_b : e.bias;
+        s_vec0[t] = (v0 && n < p.N) ? v0[n] : (e.epi == RB_EPI_COSKERNEL ? 1.f : 0.f);
+        s_vec1[t] = (e.col_scale && n < p.N) ? e.col_scale[n] : 1.f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    mbar_wait(full_bar, full_parity);
+    tc_fence_after();
+    const int nlim = min(p.N, n0 + BN);                  // columns of this tile (BN need not be a multiple of 32)
+    const int m = m0 + q * 32 + lane;
+    const int64_t orow = m < p.M ? e.map_row(m) : -1;
+    const int es_c = dtype_size(e.dtype_c);
+    const bool vec_ok = (e.ldc * es_c) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.C) % 16 == 0) &&
+                        (e.dtype_c != RB_F16S || reinterpret_cast<uintptr_t>(e.C_lo) % 16 == 0);
+#pragma unroll 1
+    for (int cb = half * 32; cb < BN; cb += 8 * EPI_WARPS) {
+        if (n0 + cb >= nlim) break;                     // warp-uniform
+        float v[32];
+        // all 32 lanes take part in the TMEM loads (.sync.aligned); rows that are not stored are masked below
+        tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + cb, v);
+        if constexpr (SPLIT) {
+            float w[32];
+            tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + BN + cb, w);
+    #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(w[j], 1.0f / 2048.0f, v[j]);
+        }
+        if (orow >= 0) {
+        const int nb = n0 + cb;
+        const bool full = nb + 32 <= nlim;
+        // every branch below is warp-uniform: the per-element work is straight-line code
+        if (e.epi == RB_EPI_COSKERNEL) {
+            const float na = e.norm_a[m];
+    #pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = nb + j;
+                const float pn = na * s_vec0[cb + j];
+                const float sc = e.cos_normalized ? pn / (pn + e.eps) : 1.0f / (pn + e.eps);
+                float r = expf((v[j] * sc - 1.0f) * e.inv_t);
+                if (m == n) r += e.diag_add;
+                v[j] = r;
+            }
+        } else {
+            if (e.alpha != 1.0f) {
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
+            }
+            if (e.bias) {
+    #pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(&s_vec0[cb + 4 * j]);
+                    v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                }
+            }
+            if (e.act == RB_ACT_RELU) {
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (e.act == RB_ACT_GELU) {
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            }
+            if (e.col_scale) {
+    #pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(&s_vec1[cb + 4 * j]);
+                    v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
+                }
+            }
+            if (e.R) {
+                if (e.dtype_r == RB_F32) {
+                    float rv[32];
+                    load_row32((const float*)e.R + orow * e.ldr + nb, rv, full, nlim - nb);
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += rv[j];
+                } else {
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < nlim) v[j] += load_any(e.R, orow * e.ldr + nb + j, e.dtype_r);
+                }
+            }
+        }
+        if (vec_ok) {
+            if (e.dtype_c == RB_F32) {
+                float* dst = (float*)e.C + orow * e.ldc + nb;
+    #pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (nb + 4 * j + 4 <= nlim) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    else {
+    #pragma unroll
+                        for (int t = 0; t < 4; ++t) if (nb + 4 * j + t < nlim) dst[4 * j + t] = v[4 * j + t];
+                    }
+                }
+            } else if (e.dtype_c == RB_F16S) {
+                // split-pair output: hi = fp16(v), lo = fp16((v - hi) * 2^11) into two planes of the same pitch
+                uint16_t* dhi = (uint16_t*)e.C + orow * e.ldc + nb;
+                uint16_t* dlo = (uint16_t*)e.C_lo + orow * e.ldc + nb;
+    #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t wh[4], wl[4];
+    #pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float x0 = v[8 * j + 2 * t], x1 = v[8 * j + 2 * t + 1];
+                        const __half2 h = __floats2half2_rn(x0, x1);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+                        wh[t] = *reinterpret_cast<const uint32_t*>(&h); wl[t] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
+                    if (nb + 8 * j + 8 <= nlim) {
+                        *reinterpret_cast<uint4*>(dhi + 8 * j) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                        *reinterpret_cast<uint4*>(dlo + 8 * j) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                    } else {
+    #pragma unroll
+                        for (int t = 0; t < 8; ++t)
+                            if (nb + 8 * j + t < nlim) {
+                                dhi[8 * j + t] = (uint16_t)(wh[t >> 1] >> (16 * (t & 1)));
+                                dlo[8 * j + t] = (uint16_t)(wl[t >> 1] >> (16 * (t & 1)));
+                            }
+                    }
+                }
+            } else {
+                uint16_t* dst = (uint16_t*)e.C + orow * e.ldc + nb;
+    #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w[4];
+    #pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        float lo = v[8 * j + 2 * t], hi = v[8 * j + 2 * t + 1];
+                        if (e.dtype_c == RB_F16) { __half2 h = __floats2half2_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
+                        else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
+                    }
+                    if (nb + 8 * j + 8 <= nlim) *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+                    else {
+    #pragma unroll
+                        for (int t = 0; t < 8; ++t)
+                            if (nb + 8 * j + t < nlim) dst[8 * j + t] = (uint16_t)(w[t >> 1] >> (16 * (t & 1)));
+                    }
+                }
+            }
+        } else {
+    #pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (nb + j < nlim) store_split_any(e.C, e.C_lo, orow * e.ldc + nb + j, e.dtype_c, v[j]);
+        }
+        }
+        __syncwarp();
+    }
+}
+
 // Persistent kernel: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (m fastest, so CTAs that run
 // together share the same weight tile in L2).  The accumulator is double-buffered in TMEM when it fits: the MMA warp
 // starts the next tile while the epilogue warps drain the previous one.
@@ -287,160 +450,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int nt = r / p.tiles_m, mt = r - nt * p.tiles_m;
             const int m0 = mt * TC_BM, n0 = nt * BN, z0 = z / p.batch1, z1 = z - z0 * p.batch1;
             const uint32_t acc = tcount % Cfg::ACC_STAGES, acc_ph = (tcount / Cfg::ACC_STAGES) & 1;
-            Epilogue e = p.epi;
-            e.C = (char*)e.C + (z0 * p.sc0 + z1 * p.sc1) * dtype_size(e.dtype_c);
-            if (e.C_lo) e.C_lo = (char*)e.C_lo + (z0 * p.sc0 + z1 * p.sc1) * 2;
-            if (e.R) e.R = (const char*)e.R + (z0 * p.sr0 + z1 * p.sr1) * dtype_size(e.dtype_r);
-            if (e.norm_a) e.norm_a += z0 * p.sna0;
-            if (e.norm_b) e.norm_b += z0 * p.snb0;
-            // stage the per-column epilogue vectors of this tile in shared memory (read back as broadcast float4s)
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");   // everyone is done with the previous tile's vectors
-            for (int t = et; t < BN; t += 32 * Cfg::EPI_WARPS) {
-                const int n = n0 + t;
-                const float* v0 = e.epi == RB_EPI_COSKERNEL ? e.norm_b : e.bias;
-                s_vec0[t] = (v0 && n < p.N) ? v0[n] : (e.epi == RB_EPI_COSKERNEL ? 1.f : 0.f);
-                s_vec1[t] = (e.col_scale && n < p.N) ? e.col_scale[n] : 1.f;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");
-            mbar_wait(&tmem_full_bar[acc], acc_ph);
-            tc_fence_after();
-            const int nlim = min(p.N, n0 + BN);                  // columns of this tile (BN need not be a multiple of 32)
-            const int m = m0 + q * 32 + lane;
-            const int64_t orow = m < p.M ? e.map_row(m) : -1;
-            const int es_c = dtype_size(e.dtype_c);
-            const bool vec_ok = (e.ldc * es_c) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.C) % 16 == 0) &&
-                                (e.dtype_c != RB_F16S || reinterpret_cast<uintptr_t>(e.C_lo) % 16 == 0);
-#pragma unroll 1
-            for (int cb = half * 32; cb < BN; cb += 8 * Cfg::EPI_WARPS) {
-                if (n0 + cb >= nlim) break;                     // warp-uniform
-                float v[32];
-                // all 32 lanes take part in the TMEM loads (.sync.aligned); rows that are not stored are masked below
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + cb, v);
-                if constexpr (SPLIT) {
-                    float w[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + BN + cb, w);
-    #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaf(w[j], 1.0f / 2048.0f, v[j]);
-                }
-                if (orow >= 0) {
-                const int nb = n0 + cb;
-                const bool full = nb + 32 <= nlim;
-                // every branch below is warp-uniform: the per-element work is straight-line code
-                if (e.epi == RB_EPI_COSKERNEL) {
-                    const float na = e.norm_a[m];
-    #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = nb + j;
-                        const float pn = na * s_vec0[cb + j];
-                        const float sc = e.cos_normalized ? pn / (pn + e.eps) : 1.0f / (pn + e.eps);
-                        float r = expf((v[j] * sc - 1.0f) * e.inv_t);
-                        if (m == n) r += e.diag_add;
-                        v[j] = r;
-                    }
-                } else {
-                    if (e.alpha != 1.0f) {
-    #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
-                    }
-                    if (e.bias) {
-    #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(&s_vec0[cb + 4 * j]);
-                            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-                        }
-                    }
-                    if (e.act == RB_ACT_RELU) {
-    #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    } else if (e.act == RB_ACT_GELU) {
-    #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                    }
-                    if (e.col_scale) {
-    #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(&s_vec1[cb + 4 * j]);
-                            v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
-                        }
-                    }
-                    if (e.R) {
-                        if (e.dtype_r == RB_F32) {
-                            float rv[32];
-                            load_row32((const float*)e.R + orow * e.ldr + nb, rv, full, nlim - nb);
-    #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] += rv[j];
-                        } else {
-    #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (nb + j < nlim) v[j] += load_any(e.R, orow * e.ldr + nb + j, e.dtype_r);
-                        }
-                    }
-                }
-                if (vec_ok) {
-                    if (e.dtype_c == RB_F32) {
-                        float* dst = (float*)e.C + orow * e.ldc + nb;
-    #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (nb + 4 * j + 4 <= nlim) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            else {
-    #pragma unroll
-                                for (int t = 0; t < 4; ++t) if (nb + 4 * j + t < nlim) dst[4 * j + t] = v[4 * j + t];
-                            }
-                        }
-                    } else if (e.dtype_c == RB_F16S) {
-                        // split-pair output: hi = fp16(v), lo = fp16((v - hi) * 2^11) into two planes of the same pitch
-                        uint16_t* dhi = (uint16_t*)e.C + orow * e.ldc + nb;
-                        uint16_t* dlo = (uint16_t*)e.C_lo + orow * e.ldc + nb;
-    #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t wh[4], wl[4];
-    #pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const float x0 = v[8 * j + 2 * t], x1 = v[8 * j + 2 * t + 1];
-                                const __half2 h = __floats2half2_rn(x0, x1);
-                                const float2 hf = __half22float2(h);
-                                const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
-                                wh[t] = *reinterpret_cast<const uint32_t*>(&h); wl[t] = *reinterpret_cast<const uint32_t*>(&l);
-                            }
-                            if (nb + 8 * j + 8 <= nlim) {
-                                *reinterpret_cast<uint4*>(dhi + 8 * j) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-                                *reinterpret_cast<uint4*>(dlo + 8 * j) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-                            } else {
-    #pragma unroll
-                                for (int t = 0; t < 8; ++t)
-                                    if (nb + 8 * j + t < nlim) {
-                                        dhi[8 * j + t] = (uint16_t)(wh[t >> 1] >> (16 * (t & 1)));
-                                        dlo[8 * j + t] = (uint16_t)(wl[t >> 1] >> (16 * (t & 1)));
-                                    }
-                            }
-                        }
-                    } else {
-                        uint16_t* dst = (uint16_t*)e.C + orow * e.ldc + nb;
-    #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t w[4];
-    #pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                float lo = v[8 * j + 2 * t], hi = v[8 * j + 2 * t + 1];
-                                if (e.dtype_c == RB_F16) { __half2 h = __floats2half2_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
-                                else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
-                            }
-                            if (nb + 8 * j + 8 <= nlim) *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
-                            else {
-    #pragma unroll
-                                for (int t = 0; t < 8; ++t)
-                                    if (nb + 8 * j + t < nlim) dst[8 * j + t] = (uint16_t)(w[t >> 1] >> (16 * (t & 1)));
-                            }
-                        }
-                    }
-                } else {
-    #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nb + j < nlim) store_split_any(e.C, e.C_lo, orow * e.ldc + nb + j, e.dtype_c, v[j]);
-                }
-                }
-                __syncwarp();
-            }
+            tc_epilogue_tile<BN, SPLIT, Cfg::EPI_WARPS>(p, tmem_base + acc * Cfg::ACC_COLS, &tmem_full_bar[acc], acc_ph, m0, n0, z0, z1, q, half, lane, et, s_vec0, s_vec1);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -448,6 +458,202 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) primitives.  Within a cluster the 32-bit shared-window address carries the CTA rank in bit 24
+// (cute::Sm100MmaPeerBitMask), so clearing that bit turns a local barrier address into the leader's (rank 0) barrier.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    // executed by both CTAs of the pair: the bytes land in the caller's shared memory, the transaction count on the LEADER's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {     // arrive on `bar` of CTA `cta` of the cluster
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+
+template <int BN, bool SPLIT> struct TcPairCfg {
+    // CTA pair = one 256 x BN tile: each CTA holds 128 rows of A and BN/2 rows of B per k-block (half the B traffic of two
+    // independent 128 x BN tiles) and its own 128 x BN accumulator rows in TMEM.
+    static constexpr int NOPS = SPLIT ? 2 : 1;
+    static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+    static constexpr int B_BYTES = (BN / 2) * TC_BK * 2;                 // this CTA's half of the B tile
+    static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
+    static constexpr int EPI_BYTES = 2 * 256 * 4;
+    static constexpr int STAGES = (232448 - 1024 - 256 - EPI_BYTES) / STAGE_BYTES > 6 ? 6 : (232448 - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
+    static constexpr int EPI_WARPS = 8;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
+    static constexpr int ACC_COLS = NOPS * BN;
+    static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;
+    static constexpr int ACC_TOTAL = ACC_STAGES * ACC_COLS;
+    static constexpr int TMEM_COLS = ACC_TOTAL <= 256 ? 256 : 512;
+    static_assert(BN % 32 == 0 && BN <= 256 && STAGES >= 2, "pair tile");
+};
+
+// Persistent CTA-pair kernel: cluster c walks pair tiles t = c, c + #clusters, ...  Rank 0 (the leader) issues every MMA
+// (tcgen05.mma.cta_group::2, M = 256); both CTAs run a TMA producer (own A rows, own half of B, signalling the leader's full
+// barrier) and epilogue warps (own 128 accumulator rows).  Barriers: full[s] leader only (armed with the bytes of both CTAs);
+// empty[s] and tmem_full[a] in both CTAs, released by multicast commits; tmem_empty[a] leader only, 2 x EPI_WARPS arrivals.
+template <int BN, bool SPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TcPairCfg<BN, SPLIT>::THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
+    using Cfg = TcPairCfg<BN, SPLIT>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
+    constexpr int OFF_A_LO = A_BYTES, OFF_B = Cfg::NOPS * A_BYTES, OFF_B_LO = Cfg::NOPS * A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;       // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    float* s_vec0 = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+    float* s_vec1 = s_vec0 + 256;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+    const int tiles_per_z = p.tiles_m * p.tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 2 * Cfg::EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();                 // both CTAs' barriers are initialised before anything signals across the pair
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    rb::pdl_wait();
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (lane == 0) {
+            const int kb_per_tap = p.ntaps > 1 ? p.k_per_tap / TC_BK : kblocks;
+            uint32_t it = 0;
+            for (int tile = cid; tile < p.total_tiles; tile += nclusters) {
+                const int z = tile / tiles_per_z, r = tile - z * tiles_per_z;
+                const int nt = r / p.tiles_m, mt = r - nt * p.tiles_m;
+                const int m0 = mt * (2 * TC_BM) + (int)rank * TC_BM, n0 = nt * BN + (int)rank * (BN / 2);
+                const int z0 = z / p.batch1, z1 = z - z0 * p.batch1;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+                    int tap = 0, kin = kb * TC_BK, shift = 0;
+                    if (p.ntaps > 1) { tap = kb / kb_per_tap; kin = (kb - tap * kb_per_tap) * TC_BK; shift = p.tap_rows[tap]; }
+                    uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                    tma_load_4d_pair(st, &map_a, &full_bar[s], kin, m0 + shift, z1, z0);
+                    if constexpr (SPLIT) tma_load_4d_pair(st + OFF_A_LO, &map_a_lo, &full_bar[s], kin, m0 + shift, z1, z0);
+                    tma_load_4d_pair(st + OFF_B, &map_b, &full_bar[s], kb * TC_BK, n0, z1, z0);
+                    if constexpr (SPLIT) tma_load_4d_pair(st + OFF_B_LO, &map_b_lo, &full_bar[s], kb * TC_BK, n0, z1, z0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (rank == 0 && lane == 0) {
+            // instruction descriptor: D=f32, A/B = f16|bf16 K-major, N>>3, M = 256 >> 4
+            uint32_t idesc = 0;
+            idesc |= 1u << 4;
+            idesc |= (uint32_t)(p.is_bf16 ? 1 : 0) << 7;
+            idesc |= (uint32_t)(p.is_bf16 ? 1 : 0) << 10;
+            idesc |= (uint32_t)(BN >> 3) << 17;
+            idesc |= (uint32_t)((2 * TC_BM) >> 4) << 24;
+            uint32_t it = 0, tcount = 0;
+            for (int tile = cid; tile < p.total_tiles; tile += nclusters, ++tcount) {
+                const uint32_t acc = tcount % Cfg::ACC_STAGES, acc_ph = (tcount / Cfg::ACC_STAGES) & 1;
+                mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);          // both CTAs' epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    const int krem = p.ntaps > 1 ? TC_BK : p.K - kb * TC_BK;
+                    const int ksteps = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        if (k < ksteps) {
+                            const uint64_t a_hi = make_smem_desc(st + k * 32, 16, 1024);
+                            const uint64_t b_hi = make_smem_desc(st + OFF_B + k * 32, 16, 1024);
+                            const uint32_t accum = (kb | k) != 0;
+                            umma_f16_pair(tmem_d, a_hi, b_hi, idesc, accum);
+                            if constexpr (SPLIT) {
+                                const uint64_t a_lo = make_smem_desc(st + OFF_A_LO + k * 32, 16, 1024);
+                                const uint64_t b_lo = make_smem_desc(st + OFF_B_LO + k * 32, 16, 1024);
+                                umma_f16_pair(tmem_d + BN, a_hi, b_lo, idesc, accum);
+                                umma_f16_pair(tmem_d + BN, a_lo, b_hi, idesc, 1u);
+                            }
+                        }
+                    }
+                    umma_commit_pair(&empty_bar[s]);          // frees the smem slot in both CTAs when these MMAs retire
+                }
+                umma_commit_pair(&tmem_full_bar[acc]);        // accumulator complete (both CTAs' epilogues)
+            }
+        }
+    } else {
+        // ===== epilogue (warps 2..9, both CTAs): this CTA's 128 rows of the pair tile =====
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;
+        uint32_t tcount = 0;
+        for (int tile = cid; tile < p.total_tiles; tile += nclusters, ++tcount) {
+            const int z = tile / tiles_per_z, r = tile - z * tiles_per_z;
+            const int nt = r / p.tiles_m, mt = r - nt * p.tiles_m;
+            const int m0 = mt * (2 * TC_BM) + (int)rank * TC_BM, n0 = nt * BN, z0 = z / p.batch1, z1 = z - z0 * p.batch1;
+            const uint32_t acc = tcount % Cfg::ACC_STAGES, acc_ph = (tcount / Cfg::ACC_STAGES) & 1;
+            tc_epilogue_tile<BN, SPLIT, Cfg::EPI_WARPS>(p, tmem_base + acc * Cfg::ACC_COLS, &tmem_full_bar[acc], acc_ph, m0, n0, z0, z1, q, half, lane, et, s_vec0, s_vec1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&tmem_empty_bar[acc], 0);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                 // the peer's shared memory and barriers stay valid until the leader's last MMA / commit
+    if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -528,6 +734,37 @@ static int launch_tc(const TcMaps& maps, TcParams& p, int zdim, cudaStream_t st)
     return check_launch("gemm_tc");
 }
 
+// 0: never, 1 (default): when profitable, 2: whenever legal (tests).  Environment variable ROMAB200_GEMM_PAIR.
+static int pair_mode() { static const int m = [] { const char* e = getenv("ROMAB200_GEMM_PAIR"); return e ? atoi(e) : 1; }(); return m; }
+
+template <int BN, bool SPLIT>
+static int launch_tc_pair(const TcMaps& maps, TcParams& p, int zdim, cudaStream_t st) {
+    using Cfg = TcPairCfg<BN, SPLIT>;
+    static bool configured[64] = {};
+    const int dev = current_device();
+    if (!configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        RB_REQUIRE(e == cudaSuccess, "gemm_tc(pair): cannot set %d bytes of dynamic shared memory: %s", Cfg::SMEM, cudaGetErrorString(e));
+        configured[dev & 63] = true;
+    }
+    p.tiles_m = (p.M + 2 * TC_BM - 1) / (2 * TC_BM);
+    p.tiles_n = (p.N + BN - 1) / BN;
+    const long long total = (long long)p.tiles_m * p.tiles_n * zdim;
+    RB_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
+    p.total_tiles = (int)total;
+    const int pairs = sm_count() / 2;
+    const int nclusters = p.total_tiles < pairs ? p.total_tiles : pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * nclusters); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = rb::pdl_mode() == 1 ? 0 : 1;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BN, SPLIT>, maps.a, maps.b, maps.a_lo, maps.b_lo, (const TcParams)p);
+    if (err != cudaSuccess) { set_error("gemm_tc(pair): launch failed: %s", cudaGetErrorString(err)); return 1; }
+    return check_launch("gemm_tc_pair");
+}
+
 template <bool SPLIT>
 static int dispatch_tc(int BN, const TcMaps& maps, TcParams& p, int zdim, cudaStream_t st) {
     switch (BN) {
@@ -577,18 +814,28 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
     // (the threshold is in tiles: below ~100 wide tiles less than 2/3 of the SMs would have work; above it the wider tile wins
     // because these shapes are bound by L2 -> shared-memory operand traffic, which a 128-wide tile raises by a third)
     if (BN > 128 && ((int64_t)((a->M + 127) / 128) * ((a->N + BN - 1) / BN) * zdim) < 100) BN = 128;
+    // CTA-pair tiles (256 x BN, tcgen05 cta_group::2): half the B-operand traffic per MMA; for the [N,K] layouts with enough
+    // 256-row tiles to fill the 74 SM pairs
+    int pair_bn = 0;
+    if (!a->trans_b && pair_mode() && (BN == 256 || BN == 192)) {
+        const long long pair_tiles = (long long)((a->M + 255) / 256) * ((a->N + BN - 1) / BN) * zdim;
+        if (pair_mode() == 2 || pair_tiles >= 40) pair_bn = BN;
+    }
     TcMaps maps;
     const uint64_t a_inner = p.ntaps > 1 ? p.k_per_tap : a->K;
     if (make_map(&maps.a, a->A, p.is_bf16, a_inner, a_rows, a->lda, p.batch1, a->sa1, batch0, a->sa0, TC_BK, TC_BM)) return 1;
     if (split && make_map(&maps.a_lo, a->A_lo, 0, a_inner, a_rows, a->lda, p.batch1, a->sa1, batch0, a->sa0, TC_BK, TC_BM)) return 1;
     if (!a->trans_b) {
-        if (make_map(&maps.b, a->B, p.is_bf16, a->K, a->N, a->ldb, p.batch1, a->sb1, batch0, a->sb0, TC_BK, BN)) return 1;
-        if (split && make_map(&maps.b_lo, a->B_lo, 0, a->K, a->N, a->ldb, p.batch1, a->sb1, batch0, a->sb0, TC_BK, BN)) return 1;
+        const uint32_t box_n = pair_bn ? pair_bn / 2 : BN;      // a CTA of a pair loads its half of the B tile
+        if (make_map(&maps.b, a->B, p.is_bf16, a->K, a->N, a->ldb, p.batch1, a->sb1, batch0, a->sb0, TC_BK, box_n)) return 1;
+        if (split && make_map(&maps.b_lo, a->B_lo, 0, a->K, a->N, a->ldb, p.batch1, a->sb1, batch0, a->sb0, TC_BK, box_n)) return 1;
     } else {
         if (make_map(&maps.b, a->B, p.is_bf16, a->N, a->K, a->ldb, p.batch1, a->sb1, batch0, a->sb0, 64, TC_BK)) return 1;
         if (split && make_map(&maps.b_lo, a->B_lo, 0, a->N, a->K, a->ldb, p.batch1, a->sb1, batch0, a->sb0, 64, TC_BK)) return 1;
     }
     if (!split) { maps.a_lo = maps.a; maps.b_lo = maps.b; }
+    if (pair_bn == 256) return split ? launch_tc_pair<256, true>(maps, p, zdim, stream) : launch_tc_pair<256, false>(maps, p, zdim, stream);
+    if (pair_bn == 192) return split ? launch_tc_pair<192, true>(maps, p, zdim, stream) : launch_tc_pair<192, false>(maps, p, zdim, stream);
     return split ? dispatch_tc<true>(BN, maps, p, zdim, stream) : dispatch_tc<false>(BN, maps, p, zdim, stream);
 }
 
