@@ -277,6 +277,10 @@ typedef struct {
 } rb_transpose_args;
 int romab200_transpose(const rb_transpose_args* args, void* stream);
 
+/* debug: role-time counters of the tcgen05 GEMM kernels, collected when the environment variable ROMAB200_TC_CLK=1 is set before
+ * the first GEMM (16 x uint64: MMA-thread / TMA-producer / epilogue wait and total cycles, tiles, k-blocks; scripts/gemm_clk.py) */
+int romab200_debug_tc_clk(unsigned long long* out, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,10 +124,17 @@ struct TcParams {
     int trans_b, is_bf16;
     int tiles_m, tiles_n, total_tiles;
     int64_t sc0, sc1, sr0, sr1, sna0, snb0;
+    unsigned long long* clk;      // optional role-time counters (ROMAB200_TC_CLK=1): see tc_clk_dump
     Epilogue epi;
 };
 
+// role-time instrumentation: cycles a role thread spent waiting / in total, summed over CTAs
+//   [0] MMA wait full   [1] MMA wait tmem_empty   [2] MMA total   [3] producer wait empty   [4] producer total
+//   [5] epilogue wait tmem_full (warp 2)   [6] epilogue total (warp 2)   [7] tiles (MMA thread)   [8] k-blocks
+__device__ __forceinline__ void clk_add(unsigned long long* clk, int i, long long v) { if (clk) atomicAdd(&clk[i], (unsigned long long)v); }
+
 constexpr int TC_BM = 128, TC_BK = 64;
+constexpr int TC_STAGE_WORDS = 32 * 20;            // epilogue transpose buffer per warp: 32 rows x 16 words, row pitch 20 words
 
 template <int BN, bool SPLIT> struct TcCfg {
     // BN = 256: one CTA per SM with 8 epilogue warps; narrower tiles: two CTAs per SM (two MMA-issuing threads keep the
@@ -137,12 +144,12 @@ template <int BN, bool SPLIT> struct TcCfg {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
-    static constexpr int STAGES = SPLIT ? (BN > 144 ? 2 : (BN > 64 ? 3 : 4))
+    static constexpr int STAGES = SPLIT ? (BN >= 144 ? 2 : (BN > 64 ? 3 : 4))
                                         : (BN >= 256 ? 4 : (BN > 128 ? 5 : (BN >= 128 ? 3 : 4)));
     static constexpr int CTAS_PER_SM = (SPLIT || BN > 128) ? 1 : 2;
     static constexpr int EPI_WARPS = BN > 128 ? 8 : 4;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
-    static constexpr int EPI_BYTES = 2 * 256 * 4;                        // staged bias / column-scale (or norm_b) of the tile
+    static constexpr int EPI_BYTES = 2 * 256 * 4 + EPI_WARPS * TC_STAGE_WORDS * 4;   // staged bias / column-scale (or norm_b) + per-warp transpose buffers
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
     static constexpr int ACC_COLS = NOPS * BN;                           // TMEM columns of one accumulator stage
     static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;       // double-buffered when it fits
@@ -156,12 +163,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 // Epilogue of one 128 x BN accumulator tile by the EPI_WARPS epilogue warps of a CTA (shared by the 1-CTA and the 2-CTA
-// kernels): stage the per-column vectors, wait for the accumulator, tcgen05.ld, fused epilogue, 16-byte stores.
+// kernels): stage the per-column vectors, wait for the accumulator, tcgen05.ld, fused epilogue, coalesced stores.
 // `tmem_acc` = TMEM address of the tile's main accumulator (lane 0); the cross accumulator of the SPLIT variant sits BN columns
 // further.  (m0, n0) = first row / column of the tile, z0 / z1 = batch indices.
+//
+// tcgen05.ld hands every lane ONE ROW of the accumulator, so a direct store writes 16-byte pieces of 32 different rows per
+// instruction: 32 cache lines touched per instruction, and measured (clock64 counters, scripts/gemm_clk.py) 16-19k cycles per
+// 128 x 256 tile against 8k (f16) / 25k (split) cycles of MMA work.  Each warp therefore transposes its 32 x 32 chunk through a
+// private 32 x 16-word staging buffer in shared memory (two halves, row pitch 20 words: conflict-free 16-byte accesses both
+// ways) and stores with 4 lanes per row: every instruction writes whole 32-byte sectors of 8 rows, and the residual operand is
+// read the same way.
+
 template <int BN, bool SPLIT, int EPI_WARPS>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, uint64_t* full_bar, uint32_t full_parity, int m0, int n0,
-                                                 int z0, int z1, int q, int half, int lane, int et, float* s_vec0, float* s_vec1) {
+                                                 int z0, int z1, int q, int half, int lane, int et, float* s_vec0, float* s_vec1, float* stage) {
     Epilogue e = p.epi;
     e.C = (char*)e.C + (z0 * p.sc0 + z1 * p.sc1) * dtype_size(e.dtype_c);
     if (e.C_lo) e.C_lo = (char*)e.C_lo + (z0 * p.sc0 + z1 * p.sc1) * 2;
@@ -177,19 +192,24 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
         s_vec1[t] = (e.col_scale && n < p.N) ? e.col_scale[n] : 1.f;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    const long long tw = clock64();
     mbar_wait(full_bar, full_parity);
+    if (p.clk && q == 2 && half == 0 && lane == 0) clk_add(p.clk, 5, clock64() - tw);
     tc_fence_after();
     const int nlim = min(p.N, n0 + BN);                  // columns of this tile (BN need not be a multiple of 32)
     const int m = m0 + q * 32 + lane;
     const int64_t orow = m < p.M ? e.map_row(m) : -1;
+    const int orow_lo = (int)(orow & 0xffffffff), orow_hi = (int)(orow >> 32);
     const int es_c = dtype_size(e.dtype_c);
     const bool vec_ok = (e.ldc * es_c) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.C) % 16 == 0) &&
                         (e.dtype_c != RB_F16S || reinterpret_cast<uintptr_t>(e.C_lo) % 16 == 0);
+    const bool rvec_ok = e.R && e.dtype_r == RB_F32 && (e.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(e.R) & 15) == 0;
+    const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;          // store phase: 4 lanes per row, 4 columns per lane
 #pragma unroll 1
     for (int cb = half * 32; cb < BN; cb += 8 * EPI_WARPS) {
         if (n0 + cb >= nlim) break;                     // warp-uniform
         float v[32];
-        // all 32 lanes take part in the TMEM loads (.sync.aligned); rows that are not stored are masked below
+        // all 32 lanes take part in the TMEM loads (.sync.aligned); rows that are not stored are masked in the store phase
         tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + cb, v);
         if constexpr (SPLIT) {
             float w[32];
@@ -197,12 +217,10 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
     #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaf(w[j], 1.0f / 2048.0f, v[j]);
         }
-        if (orow >= 0) {
         const int nb = n0 + cb;
-        const bool full = nb + 32 <= nlim;
-        // every branch below is warp-uniform: the per-element work is straight-line code
+        // ---- element-wise part in the row-per-lane layout (every branch is warp-uniform) ----
         if (e.epi == RB_EPI_COSKERNEL) {
-            const float na = e.norm_a[m];
+            const float na = m < p.M ? e.norm_a[m] : 1.f;
     #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int n = nb + j;
@@ -238,84 +256,60 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
                     v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
                 }
             }
-            if (e.R) {
-                if (e.dtype_r == RB_F32) {
-                    float rv[32];
-                    load_row32((const float*)e.R + orow * e.ldr + nb, rv, full, nlim - nb);
-    #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += rv[j];
-                } else {
-    #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nb + j < nlim) v[j] += load_any(e.R, orow * e.ldr + nb + j, e.dtype_r);
-                }
-            }
         }
-        if (vec_ok) {
-            if (e.dtype_c == RB_F32) {
-                float* dst = (float*)e.C + orow * e.ldc + nb;
+        // ---- transpose through the warp's staging buffer and store (residual added here, read coalesced) ----
     #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (nb + 4 * j + 4 <= nlim) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    else {
+        for (int h = 0; h < 2; ++h) {
+            __syncwarp();                               // the previous half has been read by every lane
     #pragma unroll
-                        for (int t = 0; t < 4; ++t) if (nb + 4 * j + t < nlim) dst[4 * j + t] = v[4 * j + t];
-                    }
-                }
-            } else if (e.dtype_c == RB_F16S) {
-                // split-pair output: hi = fp16(v), lo = fp16((v - hi) * 2^11) into two planes of the same pitch
-                uint16_t* dhi = (uint16_t*)e.C + orow * e.ldc + nb;
-                uint16_t* dlo = (uint16_t*)e.C_lo + orow * e.ldc + nb;
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(&stage[lane * 20 + 4 * j]) = make_float4(v[16 * h + 4 * j], v[16 * h + 4 * j + 1], v[16 * h + 4 * j + 2], v[16 * h + 4 * j + 3]);
+            __syncwarp();
     #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t wh[4], wl[4];
-    #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const float x0 = v[8 * j + 2 * t], x1 = v[8 * j + 2 * t + 1];
-                        const __half2 h = __floats2half2_rn(x0, x1);
-                        const float2 hf = __half22float2(h);
-                        const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
-                        wh[t] = *reinterpret_cast<const uint32_t*>(&h); wl[t] = *reinterpret_cast<const uint32_t*>(&l);
-                    }
-                    if (nb + 8 * j + 8 <= nlim) {
-                        *reinterpret_cast<uint4*>(dhi + 8 * j) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-                        *reinterpret_cast<uint4*>(dlo + 8 * j) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+            for (int it = 0; it < 4; ++it) {
+                const int r = it * 8 + sub_r;
+                const int64_t orow_r = ((int64_t)__shfl_sync(0xffffffffu, orow_hi, r) << 32) | (uint32_t)__shfl_sync(0xffffffffu, orow_lo, r);
+                const int n = nb + 16 * h + sub_c;
+                if (orow_r < 0 || n >= nlim) continue;          // no warp-synchronous operation below
+                float4 x = *reinterpret_cast<const float4*>(&stage[r * 20 + sub_c]);
+                const int nvalid = nlim - n;                    // >= 1
+                if (e.R) {
+                    if (rvec_ok && nvalid >= 4) {
+                        const float4 rr = *reinterpret_cast<const float4*>((const float*)e.R + orow_r * e.ldr + n);
+                        x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
                     } else {
+                        float* xs = reinterpret_cast<float*>(&x);
     #pragma unroll
-                        for (int t = 0; t < 8; ++t)
-                            if (nb + 8 * j + t < nlim) {
-                                dhi[8 * j + t] = (uint16_t)(wh[t >> 1] >> (16 * (t & 1)));
-                                dlo[8 * j + t] = (uint16_t)(wl[t >> 1] >> (16 * (t & 1)));
-                            }
+                        for (int t = 0; t < 4; ++t) if (t < nvalid) xs[t] += load_any(e.R, orow_r * e.ldr + n + t, e.dtype_r);
                     }
                 }
-            } else {
-                uint16_t* dst = (uint16_t*)e.C + orow * e.ldc + nb;
-    #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t w[4];
-    #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        float lo = v[8 * j + 2 * t], hi = v[8 * j + 2 * t + 1];
-                        if (e.dtype_c == RB_F16) { __half2 h = __floats2half2_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
-                        else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
+                const int64_t off = orow_r * e.ldc + n;
+                if (vec_ok && nvalid >= 4) {
+                    if (e.dtype_c == RB_F32) {
+                        *reinterpret_cast<float4*>((float*)e.C + off) = x;
+                    } else if (e.dtype_c == RB_F16S) {
+                        const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+                        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                        const __half2 l0 = __floats2half2_rn((x.x - f0.x) * 2048.0f, (x.y - f0.y) * 2048.0f);
+                        const __half2 l1 = __floats2half2_rn((x.z - f1.x) * 2048.0f, (x.w - f1.y) * 2048.0f);
+                        *reinterpret_cast<uint2*>((uint16_t*)e.C + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                        *reinterpret_cast<uint2*>((uint16_t*)e.C_lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+                    } else if (e.dtype_c == RB_F16) {
+                        const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+                        *reinterpret_cast<uint2*>((uint16_t*)e.C + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                    } else {
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+                        *reinterpret_cast<uint2*>((uint16_t*)e.C + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
                     }
-                    if (nb + 8 * j + 8 <= nlim) *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
-                    else {
+                } else {
+                    const float* xs = reinterpret_cast<const float*>(&x);
     #pragma unroll
-                        for (int t = 0; t < 8; ++t)
-                            if (nb + 8 * j + t < nlim) dst[8 * j + t] = (uint16_t)(w[t >> 1] >> (16 * (t & 1)));
-                    }
+                    for (int t = 0; t < 4; ++t) if (t < nvalid) store_split_any(e.C, e.C_lo, off + t, e.dtype_c, xs[t]);
                 }
             }
-        } else {
-    #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (nb + j < nlim) store_split_any(e.C, e.C_lo, orow * e.ldc + nb + j, e.dtype_c, v[j]);
         }
-        }
-        __syncwarp();
     }
+    __syncwarp();
 }
 
 // Persistent kernel: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (m fastest, so CTAs that run
@@ -362,6 +356,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0) {
             const int kb_per_tap = p.ntaps > 1 ? p.k_per_tap / TC_BK : kblocks;
             uint32_t it = 0;
+            long long w_empty = 0; const long long t_begin = clock64();
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int z = tile / tiles_per_z, r = tile - z * tiles_per_z;
                 const int nt = r / p.tiles_m, mt = r - nt * p.tiles_m;
@@ -369,7 +364,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    const long long tw = clock64();
                     mbar_wait(&empty_bar[s], ph ^ 1);
+                    w_empty += clock64() - tw;
                     mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
                     int tap = 0, kin = kb * TC_BK, shift = 0;
                     if (p.ntaps > 1) { tap = kb / kb_per_tap; kin = (kb - tap * kb_per_tap) * TC_BK; shift = p.tap_rows[tap]; }
@@ -389,6 +386,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
+            clk_add(p.clk, 3, w_empty); clk_add(p.clk, 4, clock64() - t_begin);
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
@@ -402,15 +400,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             idesc |= (uint32_t)(BN >> 3) << 17;
             idesc |= (uint32_t)(TC_BM >> 4) << 24;
             uint32_t it = 0, tcount = 0;
+            long long w_full = 0, w_tmem = 0; const long long t_begin = clock64();
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t acc = tcount % Cfg::ACC_STAGES, acc_ph = (tcount / Cfg::ACC_STAGES) & 1;
+                long long tw = clock64();
                 mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);          // epilogue has drained this accumulator
+                w_tmem += clock64() - tw;
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    tw = clock64();
                     mbar_wait(&full_bar[s], ph);
+                    w_full += clock64() - tw;
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
                     // k-steps that lie entirely beyond K hold TMA zero fill only: skip them (K = 24, 144, 1377 ...)
@@ -438,6 +441,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 umma_commit(&tmem_full_bar[acc]);        // accumulator complete
             }
+            clk_add(p.clk, 0, w_full); clk_add(p.clk, 1, w_tmem); clk_add(p.clk, 2, clock64() - t_begin);
+            clk_add(p.clk, 7, tcount); clk_add(p.clk, 8, it);
         }
     } else {
         // ===== epilogue (warps 2..9): TMEM lane quarter = warp % 4; the two warps of a quarter split the column chunks =====
@@ -450,10 +455,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int nt = r / p.tiles_m, mt = r - nt * p.tiles_m;
             const int m0 = mt * TC_BM, n0 = nt * BN, z0 = z / p.batch1, z1 = z - z0 * p.batch1;
             const uint32_t acc = tcount % Cfg::ACC_STAGES, acc_ph = (tcount / Cfg::ACC_STAGES) & 1;
-            tc_epilogue_tile<BN, SPLIT, Cfg::EPI_WARPS>(p, tmem_base + acc * Cfg::ACC_COLS, &tmem_full_bar[acc], acc_ph, m0, n0, z0, z1, q, half, lane, et, s_vec0, s_vec1);
+            const long long te = clock64();
+            tc_epilogue_tile<BN, SPLIT, Cfg::EPI_WARPS>(p, tmem_base + acc * Cfg::ACC_COLS, &tmem_full_bar[acc], acc_ph, m0, n0, z0, z1, q, half, lane, et, s_vec0, s_vec1, s_vec1 + 256 + (warp - 2) * TC_STAGE_WORDS);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (warp == 2 && lane == 0) clk_add(p.clk, 6, clock64() - te);
         }
     }
     __syncthreads();
@@ -513,9 +520,9 @@ template <int BN, bool SPLIT> struct TcPairCfg {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;
     static constexpr int B_BYTES = (BN / 2) * TC_BK * 2;                 // this CTA's half of the B tile
     static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
-    static constexpr int EPI_BYTES = 2 * 256 * 4;
-    static constexpr int STAGES = (232448 - 1024 - 256 - EPI_BYTES) / STAGE_BYTES > 6 ? 6 : (232448 - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
     static constexpr int EPI_WARPS = 8;
+    static constexpr int EPI_BYTES = 2 * 256 * 4 + EPI_WARPS * TC_STAGE_WORDS * 4;
+    static constexpr int STAGES = (232448 - 1024 - 256 - EPI_BYTES) / STAGE_BYTES > 6 ? 6 : (232448 - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
     static constexpr int ACC_COLS = NOPS * BN;
@@ -570,6 +577,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             const int kb_per_tap = p.ntaps > 1 ? p.k_per_tap / TC_BK : kblocks;
             uint32_t it = 0;
+            long long w_empty = 0; const long long t_begin = clock64();
             for (int tile = cid; tile < p.total_tiles; tile += nclusters) {
                 const int z = tile / tiles_per_z, r = tile - z * tiles_per_z;
                 const int nt = r / p.tiles_m, mt = r - nt * p.tiles_m;
@@ -578,7 +586,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    const long long tw = clock64();
                     mbar_wait(&empty_bar[s], ph ^ 1);
+                    w_empty += clock64() - tw;
                     if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
                     int tap = 0, kin = kb * TC_BK, shift = 0;
                     if (p.ntaps > 1) { tap = kb / kb_per_tap; kin = (kb - tap * kb_per_tap) * TC_BK; shift = p.tap_rows[tap]; }
@@ -589,6 +599,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if constexpr (SPLIT) tma_load_4d_pair(st + OFF_B_LO, &map_b_lo, &full_bar[s], kb * TC_BK, n0, z1, z0);
                 }
             }
+            clk_add(p.clk, rank ? 9 : 3, w_empty); clk_add(p.clk, rank ? 10 : 4, clock64() - t_begin);
         }
     } else if (warp == 1) {
         // ===== MMA issuer (leader CTA only) =====
@@ -601,15 +612,20 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             idesc |= (uint32_t)(BN >> 3) << 17;
             idesc |= (uint32_t)((2 * TC_BM) >> 4) << 24;
             uint32_t it = 0, tcount = 0;
+            long long w_full = 0, w_tmem = 0; const long long t_begin = clock64();
             for (int tile = cid; tile < p.total_tiles; tile += nclusters, ++tcount) {
                 const uint32_t acc = tcount % Cfg::ACC_STAGES, acc_ph = (tcount / Cfg::ACC_STAGES) & 1;
+                long long tw = clock64();
                 mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);          // both CTAs' epilogues have drained this accumulator
+                w_tmem += clock64() - tw;
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    tw = clock64();
                     mbar_wait(&full_bar[s], ph);
+                    w_full += clock64() - tw;
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
                     const int krem = p.ntaps > 1 ? TC_BK : p.K - kb * TC_BK;
@@ -633,6 +649,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
                 umma_commit_pair(&tmem_full_bar[acc]);        // accumulator complete (both CTAs' epilogues)
             }
+            clk_add(p.clk, 0, w_full); clk_add(p.clk, 1, w_tmem); clk_add(p.clk, 2, clock64() - t_begin);
+            clk_add(p.clk, 7, tcount); clk_add(p.clk, 8, it);
         }
     } else {
         // ===== epilogue (warps 2..9, both CTAs): this CTA's 128 rows of the pair tile =====
@@ -645,10 +663,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int nt = r / p.tiles_m, mt = r - nt * p.tiles_m;
             const int m0 = mt * (2 * TC_BM) + (int)rank * TC_BM, n0 = nt * BN, z0 = z / p.batch1, z1 = z - z0 * p.batch1;
             const uint32_t acc = tcount % Cfg::ACC_STAGES, acc_ph = (tcount / Cfg::ACC_STAGES) & 1;
-            tc_epilogue_tile<BN, SPLIT, Cfg::EPI_WARPS>(p, tmem_base + acc * Cfg::ACC_COLS, &tmem_full_bar[acc], acc_ph, m0, n0, z0, z1, q, half, lane, et, s_vec0, s_vec1);
+            const long long te = clock64();
+            tc_epilogue_tile<BN, SPLIT, Cfg::EPI_WARPS>(p, tmem_base + acc * Cfg::ACC_COLS, &tmem_full_bar[acc], acc_ph, m0, n0, z0, z1, q, half, lane, et, s_vec0, s_vec1, s_vec1 + 256 + (warp - 2) * TC_STAGE_WORDS);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(&tmem_empty_bar[acc], 0);
+            if (warp == 2 && lane == 0 && rank == 0) clk_add(p.clk, 6, clock64() - te);
         }
     }
     tc_fence_before();
@@ -694,6 +714,17 @@ static int make_map(CUtensorMap* map, const void* base, int is_bf16, uint64_t in
 }
 
 struct TcMaps { CUtensorMap a, b, a_lo, b_lo; };
+
+static unsigned long long* tc_clk_buffer() {        // ROMAB200_TC_CLK=1: role-time counters in a device buffer (debug)
+    static unsigned long long* buf = nullptr;
+    static int init = 0;
+    if (!init) {
+        init = 1;
+        const char* e = getenv("ROMAB200_TC_CLK");
+        if (e && atoi(e)) { if (cudaMalloc(&buf, 16 * sizeof(unsigned long long)) != cudaSuccess) buf = nullptr; else cudaMemset(buf, 0, 16 * sizeof(unsigned long long)); }
+    }
+    return buf;
+}
 
 static int sm_count() {
     static int n[64] = {};
@@ -793,6 +824,7 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
     p.trans_b = a->trans_b; p.is_bf16 = a->dtype_ab == RB_BF16;
     p.sc0 = a->sc0; p.sc1 = a->sc1; p.sr0 = a->sr0; p.sr1 = a->sr1; p.sna0 = a->sna0; p.snb0 = a->snb0;
     p.epi = make_epilogue(a);
+    p.clk = tc_clk_buffer();
     if (p.ntaps > 1) {
         RB_REQUIRE(a->K % p.ntaps == 0 && p.k_per_tap % TC_BK == 0, "gemm_tc: K/ntaps=%d must be a multiple of %d", p.k_per_tap, TC_BK);
         RB_REQUIRE(!a->trans_b && batch0 * p.batch1 == 1, "gemm_tc: taps need un-batched [N,K] weights");
@@ -814,6 +846,10 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
     // (the threshold is in tiles: below ~100 wide tiles less than 2/3 of the SMs would have work; above it the wider tile wins
     // because these shapes are bound by L2 -> shared-memory operand traffic, which a 128-wide tile raises by a third)
     if (BN > 128 && ((int64_t)((a->M + 127) / 128) * ((a->N + BN - 1) / BN) * zdim) < 100) BN = 128;
+    {   // experiments: ROMAB200_GEMM_BN forces the tile width of the [N,K] layouts when it is one of the instantiated widths
+        static const int force_bn = [] { const char* e = getenv("ROMAB200_GEMM_BN"); return e ? atoi(e) : 0; }();
+        if (force_bn && !a->trans_b && (force_bn == 32 || force_bn == 64 || force_bn == 128 || force_bn == 144 || force_bn == 192 || force_bn == 256)) BN = force_bn;
+    }
     // CTA-pair tiles (256 x BN, tcgen05 cta_group::2): half the B-operand traffic per MMA; for the [N,K] layouts with enough
     // 256-row tiles to fill the 74 SM pairs
     int pair_bn = 0;
@@ -840,3 +876,12 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
 }
 
 }  // namespace rb
+
+// debug: read (and optionally reset) the role-time counters collected with ROMAB200_TC_CLK=1 (16 x u64, see gemm_tc.cu)
+extern "C" int romab200_debug_tc_clk(unsigned long long* out, int reset) {
+    unsigned long long* buf = rb::tc_clk_buffer();
+    if (!buf) return 1;
+    if (cudaMemcpy(out, buf, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 2;
+    if (reset) cudaMemset(buf, 0, 16 * sizeof(unsigned long long));
+    return 0;
+}
