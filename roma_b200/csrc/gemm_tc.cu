@@ -52,6 +52,21 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// TMA stores (UTMASTG): shared -> global through a tensor map, tracked by bulk async-groups of the issuing thread
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// the same as an element-wise fp32 reduction into global memory: C += tile (the in-place residual update)
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -125,6 +140,8 @@ struct TcParams {
     int tiles_m, tiles_n, total_tiles;
     int64_t sc0, sc1, sr0, sr1, sna0, snb0;
     unsigned long long* clk;      // optional role-time counters (ROMAB200_TC_CLK=1): see tc_clk_dump
+    int epi_mode;                 // store strategy of the epilogue: 0 = direct row-per-lane stores, 1 = shared-memory transpose,
+                                  // 2 = TMA stores from a per-warp staging buffer (map_c / map_c_lo), 3 = the same as an fp32 reduce-add (C += tile)
     Epilogue epi;
 };
 
@@ -176,7 +193,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 template <int BN, bool SPLIT, int EPI_WARPS>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, uint64_t* full_bar, uint32_t full_parity, int m0, int n0,
-                                                 int z0, int z1, int q, int half, int lane, int et, float* s_vec0, float* s_vec1, float* stage) {
+                                                 int z0, int z1, int q, int half, int lane, int et, float* s_vec0, float* s_vec1, float* stage,
+                                                 const CUtensorMap* map_c, const CUtensorMap* map_c_lo) {
+    const long long t_entry = clock64();
     Epilogue e = p.epi;
     e.C = (char*)e.C + (z0 * p.sc0 + z1 * p.sc1) * dtype_size(e.dtype_c);
     if (e.C_lo) e.C_lo = (char*)e.C_lo + (z0 * p.sc0 + z1 * p.sc1) * 2;
@@ -192,9 +211,12 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
         s_vec1[t] = (e.col_scale && n < p.N) ? e.col_scale[n] : 1.f;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    const bool timing = p.clk && q == 2 && half == 0 && lane == 0;     // warp 2, lane 0
     const long long tw = clock64();
+    const long long t_pre = tw - t_entry;
+    long long t_ld = 0, t_math = 0, t_store = 0;
     mbar_wait(full_bar, full_parity);
-    if (p.clk && q == 2 && half == 0 && lane == 0) clk_add(p.clk, 5, clock64() - tw);
+    if (timing) clk_add(p.clk, 5, clock64() - tw);
     tc_fence_after();
     const int nlim = min(p.N, n0 + BN);                  // columns of this tile (BN need not be a multiple of 32)
     const int m = m0 + q * 32 + lane;
@@ -209,6 +231,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
     for (int cb = half * 32; cb < BN; cb += 8 * EPI_WARPS) {
         if (n0 + cb >= nlim) break;                     // warp-uniform
         float v[32];
+        const long long tc0 = clock64();
         // all 32 lanes take part in the TMEM loads (.sync.aligned); rows that are not stored are masked in the store phase
         tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + cb, v);
         if constexpr (SPLIT) {
@@ -218,6 +241,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
             for (int j = 0; j < 32; ++j) v[j] = fmaf(w[j], 1.0f / 2048.0f, v[j]);
         }
         const int nb = n0 + cb;
+        const long long tc1 = clock64();
+        t_ld += tc1 - tc0;
         // ---- element-wise part in the row-per-lane layout (every branch is warp-uniform) ----
         if (e.epi == RB_EPI_COSKERNEL) {
             const float na = m < p.M ? e.norm_a[m] : 1.f;
@@ -258,6 +283,157 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
             }
         }
         // ---- transpose through the warp's staging buffer and store (residual added here, read coalesced) ----
+        long long tc2 = clock64();
+        t_math += tc2 - tc1;
+        if (p.epi_mode >= 2) {
+            // ---- TMA stores: the warp's 32 x 32 chunk goes through its 2 KB staging buffer as [32 rows][64 B] (16-bit output: one
+            // round of 32 columns; fp32 / split pair: two rounds of 16 columns) and leaves with cp.async.bulk.tensor: whole segments,
+            // clipped at the M / N tails by the tensor map, asynchronous to the warp.  Rows that are not stored (the zero border of a
+            // padded map) are written as zeros, which is what they hold already.
+            if (orow < 0) {
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
+            const int row0 = m0 + q * 32;
+            if (e.dtype_c == RB_F16 || e.dtype_c == RB_BF16) {
+                if (lane == 0) bulk_wait_read();
+                __syncwarp();
+    #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w[4];
+    #pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float lo = v[8 * j + 2 * t], hi = v[8 * j + 2 * t + 1];
+                        if (e.dtype_c == RB_F16) { __half2 hh = __floats2half2_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&hh); }
+                        else { __nv_bfloat162 hh = __floats2bfloat162_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&hh); }
+                    }
+                    *reinterpret_cast<uint4*>(sb + lane * 64 + 16 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) { tma_store_4d(map_c, sb, nb, row0, z1, z0); bulk_commit(); }
+            } else {
+    #pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (nb + 16 * h >= nlim) break;                 // warp-uniform
+                    if (lane == 0) bulk_wait_read();
+                    __syncwarp();
+                    if (e.dtype_c == RB_F32) {
+    #pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<float4*>(sb + lane * 64 + 16 * j) = make_float4(v[16 * h + 4 * j], v[16 * h + 4 * j + 1], v[16 * h + 4 * j + 2], v[16 * h + 4 * j + 3]);
+                    } else {                                        // RB_F16S: hi rows at [0, 1 KB), lo rows at [1 KB, 2 KB), 32 B each
+    #pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            uint32_t wh[4], wl[4];
+    #pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float x0 = v[16 * h + 8 * j + 2 * t], x1 = v[16 * h + 8 * j + 2 * t + 1];
+                                const __half2 hh = __floats2half2_rn(x0, x1);
+                                const float2 hf = __half22float2(hh);
+                                const __half2 ll = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+                                wh[t] = *reinterpret_cast<const uint32_t*>(&hh); wl[t] = *reinterpret_cast<const uint32_t*>(&ll);
+                            }
+                            *reinterpret_cast<uint4*>(sb + lane * 32 + 16 * j) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                            *reinterpret_cast<uint4*>(sb + 1024 + lane * 32 + 16 * j) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                        }
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (e.dtype_c == RB_F32) {
+                            if (p.epi_mode == 3) tma_reduce_add_4d(map_c, sb, nb + 16 * h, row0, z1, z0);
+                            else tma_store_4d(map_c, sb, nb + 16 * h, row0, z1, z0);
+                        } else {
+                            tma_store_4d(map_c, sb, nb + 16 * h, row0, z1, z0);
+                            tma_store_4d(map_c_lo, sb + 1024, nb + 16 * h, row0, z1, z0);
+                        }
+                        bulk_commit();
+                    }
+                }
+            }
+        } else if (p.epi_mode == 0) {
+            if (orow >= 0) {
+            const bool full = nb + 32 <= nlim;
+            if (e.epi != RB_EPI_COSKERNEL) {
+            if (e.R) {
+                if (e.dtype_r == RB_F32) {
+                    float rv[32];
+                    load_row32((const float*)e.R + orow * e.ldr + nb, rv, full, nlim - nb);
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += rv[j];
+                } else {
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < nlim) v[j] += load_any(e.R, orow * e.ldr + nb + j, e.dtype_r);
+                }
+            }
+            }
+        if (vec_ok) {
+            if (e.dtype_c == RB_F32) {
+                float* dst = (float*)e.C + orow * e.ldc + nb;
+    #pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (nb + 4 * j + 4 <= nlim) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    else {
+    #pragma unroll
+                        for (int t = 0; t < 4; ++t) if (nb + 4 * j + t < nlim) dst[4 * j + t] = v[4 * j + t];
+                    }
+                }
+            } else if (e.dtype_c == RB_F16S) {
+                // split-pair output: hi = fp16(v), lo = fp16((v - hi) * 2^11) into two planes of the same pitch
+                uint16_t* dhi = (uint16_t*)e.C + orow * e.ldc + nb;
+                uint16_t* dlo = (uint16_t*)e.C_lo + orow * e.ldc + nb;
+    #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t wh[4], wl[4];
+    #pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float x0 = v[8 * j + 2 * t], x1 = v[8 * j + 2 * t + 1];
+                        const __half2 h = __floats2half2_rn(x0, x1);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+                        wh[t] = *reinterpret_cast<const uint32_t*>(&h); wl[t] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
+                    if (nb + 8 * j + 8 <= nlim) {
+                        *reinterpret_cast<uint4*>(dhi + 8 * j) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                        *reinterpret_cast<uint4*>(dlo + 8 * j) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                    } else {
+    #pragma unroll
+                        for (int t = 0; t < 8; ++t)
+                            if (nb + 8 * j + t < nlim) {
+                                dhi[8 * j + t] = (uint16_t)(wh[t >> 1] >> (16 * (t & 1)));
+                                dlo[8 * j + t] = (uint16_t)(wl[t >> 1] >> (16 * (t & 1)));
+                            }
+                    }
+                }
+            } else {
+                uint16_t* dst = (uint16_t*)e.C + orow * e.ldc + nb;
+    #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w[4];
+    #pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        float lo = v[8 * j + 2 * t], hi = v[8 * j + 2 * t + 1];
+                        if (e.dtype_c == RB_F16) { __half2 h = __floats2half2_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
+                        else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); w[t] = *reinterpret_cast<uint32_t*>(&h); }
+                    }
+                    if (nb + 8 * j + 8 <= nlim) *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+                    else {
+    #pragma unroll
+                        for (int t = 0; t < 8; ++t)
+                            if (nb + 8 * j + t < nlim) dst[8 * j + t] = (uint16_t)(w[t >> 1] >> (16 * (t & 1)));
+                    }
+                }
+            }
+        } else {
+    #pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (nb + j < nlim) store_split_any(e.C, e.C_lo, orow * e.ldc + nb + j, e.dtype_c, v[j]);
+        }
+            }
+        } else {
     #pragma unroll
         for (int h = 0; h < 2; ++h) {
             __syncwarp();                               // the previous half has been read by every lane
@@ -308,7 +484,17 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
                 }
             }
         }
+        }
+        __syncwarp();
+        if (timing) { t_store += clock64() - tc2; }
     }
+    if (timing) { clk_add(p.clk, 11, t_pre); clk_add(p.clk, 12, t_ld); clk_add(p.clk, 13, t_math); clk_add(p.clk, 14, t_store); }
+    __syncwarp();
+}
+
+// called by every epilogue warp before the CTA exits: the bulk stores it issued have completed
+__device__ __forceinline__ void tc_epilogue_drain(const TcParams& p, int lane) {
+    if (p.epi_mode >= 2 && lane == 0) bulk_wait_all();
     __syncwarp();
 }
 
@@ -318,7 +504,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(TcCfg<BN, SPLIT>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo,
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c_lo, const TcParams p) {
     using Cfg = TcCfg<BN, SPLIT>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
@@ -456,12 +643,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int m0 = mt * TC_BM, n0 = nt * BN, z0 = z / p.batch1, z1 = z - z0 * p.batch1;
             const uint32_t acc = tcount % Cfg::ACC_STAGES, acc_ph = (tcount / Cfg::ACC_STAGES) & 1;
             const long long te = clock64();
-            tc_epilogue_tile<BN, SPLIT, Cfg::EPI_WARPS>(p, tmem_base + acc * Cfg::ACC_COLS, &tmem_full_bar[acc], acc_ph, m0, n0, z0, z1, q, half, lane, et, s_vec0, s_vec1, s_vec1 + 256 + (warp - 2) * TC_STAGE_WORDS);
+            tc_epilogue_tile<BN, SPLIT, Cfg::EPI_WARPS>(p, tmem_base + acc * Cfg::ACC_COLS, &tmem_full_bar[acc], acc_ph, m0, n0, z0, z1, q, half, lane, et, s_vec0, s_vec1, s_vec1 + 256 + (warp - 2) * TC_STAGE_WORDS, &map_c, &map_c_lo);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
             if (warp == 2 && lane == 0) clk_add(p.clk, 6, clock64() - te);
         }
+        tc_epilogue_drain(p, lane);
     }
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
@@ -539,7 +727,8 @@ template <int BN, bool SPLIT> struct TcPairCfg {
 template <int BN, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TcPairCfg<BN, SPLIT>::THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
+                    const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo,
+                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c_lo, const TcParams p) {
     using Cfg = TcPairCfg<BN, SPLIT>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
@@ -664,12 +853,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int m0 = mt * (2 * TC_BM) + (int)rank * TC_BM, n0 = nt * BN, z0 = z / p.batch1, z1 = z - z0 * p.batch1;
             const uint32_t acc = tcount % Cfg::ACC_STAGES, acc_ph = (tcount / Cfg::ACC_STAGES) & 1;
             const long long te = clock64();
-            tc_epilogue_tile<BN, SPLIT, Cfg::EPI_WARPS>(p, tmem_base + acc * Cfg::ACC_COLS, &tmem_full_bar[acc], acc_ph, m0, n0, z0, z1, q, half, lane, et, s_vec0, s_vec1, s_vec1 + 256 + (warp - 2) * TC_STAGE_WORDS);
+            tc_epilogue_tile<BN, SPLIT, Cfg::EPI_WARPS>(p, tmem_base + acc * Cfg::ACC_COLS, &tmem_full_bar[acc], acc_ph, m0, n0, z0, z1, q, half, lane, et, s_vec0, s_vec1, s_vec1 + 256 + (warp - 2) * TC_STAGE_WORDS, &map_c, &map_c_lo);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(&tmem_empty_bar[acc], 0);
             if (warp == 2 && lane == 0 && rank == 0) clk_add(p.clk, 6, clock64() - te);
         }
+        tc_epilogue_drain(p, lane);
     }
     tc_fence_before();
     cluster_sync_all();                 // the peer's shared memory and barriers stay valid until the leader's last MMA / commit
@@ -694,6 +884,10 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// 4-D map over (columns, rows, batch1, batch0) of an OUTPUT matrix for the TMA-store epilogue: no swizzle, box = box_cols x 32 rows
+static int make_out_map(CUtensorMap* map, void* base, int dtype, uint64_t cols, uint64_t rows, uint64_t pitch_elems, uint64_t b1, uint64_t s1_elems,
+                        uint64_t b0, uint64_t s0_elems, uint32_t box_cols);
+
 // 4-D map over (inner, rows, batch1, batch0) of a 16-bit matrix
 static int make_map(CUtensorMap* map, const void* base, int is_bf16, uint64_t inner, uint64_t rows, uint64_t pitch_elems, uint64_t b1,
                     uint64_t s1_elems, uint64_t b0, uint64_t s0_elems, uint32_t box_inner, uint32_t box_rows) {
@@ -713,7 +907,24 @@ static int make_map(CUtensorMap* map, const void* base, int is_bf16, uint64_t in
     return 0;
 }
 
-struct TcMaps { CUtensorMap a, b, a_lo, b_lo; };
+static int make_out_map(CUtensorMap* map, void* base, int dtype, uint64_t cols, uint64_t rows, uint64_t pitch_elems, uint64_t b1, uint64_t s1_elems,
+                        uint64_t b0, uint64_t s0_elems, uint32_t box_cols) {
+    EncodeTiledFn enc = get_encode();
+    RB_REQUIRE(enc, "gemm_tc: cuTensorMapEncodeTiled not available (driver too old?)");
+    const uint64_t es = dtype == RB_F32 ? 4 : 2;
+    cuuint64_t dims[4] = {cols, rows, b1 > 0 ? b1 : 1, b0 > 0 ? b0 : 1};
+    cuuint64_t strides[3] = {pitch_elems * es, (b1 > 1 ? s1_elems : pitch_elems * rows) * es, (b0 > 1 ? s0_elems : pitch_elems * rows) * es};
+    cuuint32_t box[4] = {box_cols, 32, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUtensorMapDataType dt = dtype == RB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (dtype == RB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    CUresult r = enc(map, dt, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RB_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled (output) failed with %d (cols=%llu rows=%llu pitch=%llu)", (int)r,
+               (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch_elems);
+    return 0;
+}
+
+struct TcMaps { CUtensorMap a, b, a_lo, b_lo, c, c_lo; };
 
 static unsigned long long* tc_clk_buffer() {        // ROMAB200_TC_CLK=1: role-time counters in a device buffer (debug)
     static unsigned long long* buf = nullptr;
@@ -760,7 +971,7 @@ static int launch_tc(const TcMaps& maps, TcParams& p, int zdim, cudaStream_t st)
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = rb::pdl_mode() == 1 ? 0 : 1;
-    cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, SPLIT>, maps.a, maps.b, maps.a_lo, maps.b_lo, (const TcParams)p);
+    cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, SPLIT>, maps.a, maps.b, maps.a_lo, maps.b_lo, maps.c, maps.c_lo, (const TcParams)p);
     if (err != cudaSuccess) { set_error("gemm_tc: launch failed: %s", cudaGetErrorString(err)); return 1; }
     return check_launch("gemm_tc");
 }
@@ -791,7 +1002,7 @@ static int launch_tc_pair(const TcMaps& maps, TcParams& p, int zdim, cudaStream_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = rb::pdl_mode() == 1 ? 0 : 1;
-    cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BN, SPLIT>, maps.a, maps.b, maps.a_lo, maps.b_lo, (const TcParams)p);
+    cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BN, SPLIT>, maps.a, maps.b, maps.a_lo, maps.b_lo, maps.c, maps.c_lo, (const TcParams)p);
     if (err != cudaSuccess) { set_error("gemm_tc(pair): launch failed: %s", cudaGetErrorString(err)); return 1; }
     return check_launch("gemm_tc_pair");
 }
@@ -825,6 +1036,7 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
     p.sc0 = a->sc0; p.sc1 = a->sc1; p.sr0 = a->sr0; p.sr1 = a->sr1; p.sna0 = a->sna0; p.snb0 = a->snb0;
     p.epi = make_epilogue(a);
     p.clk = tc_clk_buffer();
+    { static const int em = [] { const char* e = getenv("ROMAB200_GEMM_EPI"); return e ? atoi(e) : 2; }(); p.epi_mode = em; }
     if (p.ntaps > 1) {
         RB_REQUIRE(a->K % p.ntaps == 0 && p.k_per_tap % TC_BK == 0, "gemm_tc: K/ntaps=%d must be a multiple of %d", p.k_per_tap, TC_BK);
         RB_REQUIRE(!a->trans_b && batch0 * p.batch1 == 1, "gemm_tc: taps need un-batched [N,K] weights");
@@ -870,6 +1082,27 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
         if (split && make_map(&maps.b_lo, a->B_lo, 0, a->N, a->K, a->ldb, p.batch1, a->sb1, batch0, a->sb0, 64, TC_BK)) return 1;
     }
     if (!split) { maps.a_lo = maps.a; maps.b_lo = maps.b; }
+    // TMA-store epilogue when the output is a plain (or zero-bordered) matrix with 16-byte aligned pitches; an in-place fp32 residual
+    // (R == C: the residual stream, the GP trailing update) becomes a reduce-add.  Otherwise the per-lane direct stores.
+    maps.c = maps.a; maps.c_lo = maps.a;
+    {
+        const int es_c = a->dtype_c == RB_F32 ? 4 : 2;
+        const bool align_ok = ((uintptr_t)a->C) % 16 == 0 && (a->ldc * es_c) % 16 == 0 && (p.batch1 <= 1 || (a->sc1 * es_c) % 16 == 0) &&
+                              (batch0 <= 1 || (a->sc0 * es_c) % 16 == 0) && (a->dtype_c != RB_F16S || ((uintptr_t)a->C_lo) % 16 == 0);
+        const bool rowmap_ok = a->rowmap == RB_ROWMAP_NONE || a->rowmap == RB_ROWMAP_PAD_KEEP;
+        const bool inplace_r = a->R && a->R == a->C && a->dtype_r == RB_F32 && a->dtype_c == RB_F32 && a->ldr == a->ldc && a->sr0 == a->sc0 && a->sr1 == a->sc1 &&
+                               a->epi == RB_EPI_LINEAR;
+        if (p.epi_mode >= 2 && align_ok && rowmap_ok && (!a->R || inplace_r)) {
+            const uint32_t box_cols = (a->dtype_c == RB_F16 || a->dtype_c == RB_BF16) ? 32 : 16;
+            const int dt = a->dtype_c == RB_F16S ? RB_F16 : a->dtype_c;
+            if (make_out_map(&maps.c, a->C, dt, a->N, a->M, a->ldc, p.batch1, a->sc1, batch0, a->sc0, box_cols)) return 1;
+            if (a->dtype_c == RB_F16S && make_out_map(&maps.c_lo, a->C_lo, RB_F16, a->N, a->M, a->ldc, p.batch1, a->sc1, batch0, a->sc0, box_cols)) return 1;
+            p.epi_mode = inplace_r ? 3 : 2;
+            if (inplace_r) p.epi.R = nullptr;           // the reduction adds it
+        } else if (p.epi_mode >= 2) {
+            p.epi_mode = 0;
+        }
+    }
     if (pair_bn == 256) return split ? launch_tc_pair<256, true>(maps, p, zdim, stream) : launch_tc_pair<256, false>(maps, p, zdim, stream);
     if (pair_bn == 192) return split ? launch_tc_pair<192, true>(maps, p, zdim, stream) : launch_tc_pair<192, false>(maps, p, zdim, stream);
     return split ? dispatch_tc<true>(BN, maps, p, zdim, stream) : dispatch_tc<false>(BN, maps, p, zdim, stream);

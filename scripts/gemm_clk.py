@@ -35,8 +35,11 @@ def run(name, M, N, K, split, act=0, reps=5):
     v = [x / reps for x in out]
     tiles, kb = max(v[7], 1), max(v[8], 1)
     n_mma = 74 if v[9] > 0 else 148        # MMA threads: one per pair or one per CTA (approx., full grid)
+    ew = tiles * (2 if v[9] > 0 else 1)        # epilogue-timing warps: warp 2 of every CTA
+    print(f"    epilogue phases per tile [cycles] (EPI={os.environ.get('ROMAB200_GEMM_EPI', '1')}): pre(vectors+barriers) {v[11] / ew:.0f}, wait acc {v[5] / ew:.0f}, "
+          f"tmem ld {v[12] / ew:.0f}, math {v[13] / ew:.0f}, store {v[14] / ew:.0f}")
     print(f"{name}: {s.elapsed_time(e) / reps * 1e3:.1f} us; per k-block [cycles]: mma total {v[2] / kb:.0f}, wait full {v[0] / kb:.0f}, wait tmem {v[1] / kb:.0f}; "
-          f"prod0 wait empty {v[3] / kb:.0f} of {v[4] / kb:.0f}; per tile: epi total {v[6] / tiles * (2 if v[9] > 0 else 1):.0f} wait {v[5] / tiles * (2 if v[9] > 0 else 1):.0f}; tiles {tiles:.0f} kblocks {kb:.0f}", flush=True)
+          f"prod0 wait empty {v[3] / kb:.0f} of {v[4] / kb:.0f}; per tile: epi total {v[6] / tiles:.0f}; tiles {tiles:.0f} kblocks {kb:.0f}", flush=True)
 
 
 print("PAIR =", os.environ.get("ROMAB200_GEMM_PAIR", "1"))
@@ -44,4 +47,4 @@ for split in (True, False):
     t = "split" if split else "fp16 "
     run(f"{t} fc1 3202x4096x1024 gelu", 3202, 4096, 1024, split, cabi.ACT_GELU)
     run(f"{t} qkv 3202x3072x1024", 3202, 3072, 1024, split)
-    run(f"{t} big 8192^3", 8192, 8192, 8192, split, reps=2)
+    run(f"{t} fc2->f32 3202x1024x4096", 3202, 1024, 4096, split)
