@@ -111,6 +111,68 @@ def cpu_reference_time(steps, warmup, budget_s=240.0, with_sample=True):
     return times, torch.get_num_threads()
 
 
+def torch_cuda_baseline(dev, steps=5, warmup=2, with_sample=True):
+    """The "existing Blackwell kernels" bar: the same graph through stock PyTorch on this GPU — the oracle's
+    torch.nn.functional restatement of the reference with weights and inputs on `cuda`, i.e. cuDNN convolutions, cuBLAS GEMMs, SDPA
+    attention, cuSOLVER Cholesky, ATen grid_sample — once in fp32 (TF32 off) and once under fp16 autocast with the GP kept in fp32
+    (the reference's CUDA regime, utils.py:639-653, approximately).  A comparison leg only: nothing of the product runs here."""
+    import torch
+    from oracle.roma_oracle import RomaOracle
+    from roma_b200 import synthetic
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    mw, dw = synthetic.make_weights(0)
+    orc = RomaOracle(mw, dw, COARSE, UPSAMPLE, device=dev)
+    A, B, Ah, Bh = (t.to(dev) for t in synthetic.make_pair(1, COARSE, UPSAMPLE, seed=1))
+    stage_ev = {}
+
+    def wrap(name, fn):
+        def inner(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(*a, **k)
+            e.record()
+            stage_ev.setdefault(name, []).append((s, e))
+            return out
+        return inner
+    gp_fp32 = orc.gp
+
+    def gp_no_autocast(x, y):
+        with torch.autocast("cuda", enabled=False):
+            return gp_fp32(x.float(), y.float())
+    orc.gp = wrap("gp", gp_no_autocast)
+    orc.vgg, orc.dinov2 = wrap("vgg", orc.vgg), wrap("dinov2", orc.dinov2)
+    orc.embedding_decoder = wrap("decoder transformer", orc.embedding_decoder)
+    ref_fn = orc.conv_refiner
+    orc.conv_refiner = lambda s, *a, **k: wrap(f"refine{s}", ref_fn)(s, *a, **k)
+    out = {}
+    for label, ctx in (("fp32", lambda: torch.autocast("cuda", enabled=False)), ("fp16_autocast", lambda: torch.autocast("cuda", dtype=torch.float16))):
+        def step():
+            with torch.inference_mode(), ctx():
+                w, c = orc.match(A, B, Ah, Bh)
+            if with_sample:
+                orc.sample(w[0].float(), c[0].float(), num=10000)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        stage_ev.clear()
+        ev = []
+        for _ in range(steps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); step(); e.record()
+            ev.append((s, e))
+        torch.cuda.synchronize()
+        ms = sum(s.elapsed_time(e) for s, e in ev) / steps
+        out[label] = {"value": 1e3 / ms, "unit": "pairs/s", "ms_per_step": ms,
+                      "stage_ms_per_step": {k: round(sum(s.elapsed_time(e) for s, e in v) / steps, 3) for k, v in stage_ev.items()}}
+    out["what"] = ("stock PyTorch " + torch.__version__ + " on the same GPU: oracle/roma_oracle.py (torch.nn.functional restatement of the reference, "
+                   "bit-exact vs it on CPU) with weights and inputs on cuda: cuDNN / cuBLAS / SDPA / cuSOLVER / ATen kernels; 1 pair per step, "
+                   "CUDA events, TF32 off; fp16_autocast keeps the GP in fp32")
+    del orc
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -136,7 +198,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from roma_b200 import cabi, roma_outdoor, synthetic
+    from roma_b200 import cabi, roma_indoor, roma_outdoor, sharding, synthetic
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -164,37 +226,72 @@ def run_ours(args):
             os.close(saved_fd)
     from roma_b200 import model_zoo
     amp = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32, "fp32_simt": torch.float32}[args.precision]
-    mw, dw = synthetic.make_weights(0)
+    factory, wseed = (roma_indoor, 1) if args.model == "indoor" else (roma_outdoor, 0)      # same graph, different checkpoint (model_zoo/__init__.py:8-9)
+    mw, dw = synthetic.make_weights(wseed)
     model_zoo.fp32_backend = "simt" if args.precision == "fp32_simt" else "tcgen05"
-    model = roma_outdoor(dev, weights=mw, dinov2_weights=dw, coarse_res=COARSE, upsample_res=UPSAMPLE, amp_dtype=amp)
+    model = factory(dev, weights=mw, dinov2_weights=dw, coarse_res=COARSE, upsample_res=UPSAMPLE, amp_dtype=amp)
     assert model.engine.precision == args.precision
-    P = args.pairs_per_gpu
-    A, B, Ah, Bh = synthetic.make_pair(P, COARSE, UPSAMPLE, seed=1 + rank)
-    host = [t.pin_memory() for t in (A, B, Ah, Bh)]
-    devt = [t.to(dev) for t in (A, B, Ah, Bh)]
+    P = args.pairs_per_gpu                       # pairs per match() call on one GPU
+    G = args.global_pairs or P * world           # pairs per step over the whole job
+    # N > 1: rank 0 owns the batch of a step; the inputs are scattered and the warps / certainties gathered over NCCL INSIDE the
+    # timed region.  --no-scatter keeps every rank on its own resident pairs (no collective on the data path).
+    sharded = world > 1 and not args.no_scatter
+    if sharded or world == 1:
+        lo, hi = sharding.shard_bounds(G, world)[rank]
+        src_pairs = synthetic.make_pair(G, COARSE, UPSAMPLE, seed=1) if rank == 0 else None
+    else:
+        lo, hi = 0, G // world
+        src_pairs = synthetic.make_pair(hi, COARSE, UPSAMPLE, seed=1 + rank)
+    host = [t.pin_memory() for t in src_pairs] if src_pairs is not None else None
+    devt = [t.to(dev) for t in src_pairs] if src_pairs is not None else None
+    del src_pairs
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
     out_host = None
+    d2h_samples = [0]
+
+    def sample_batch(warp, cert, to_host=False):
+        if args.no_sample:
+            return
+        for i in range(warp.shape[0]):
+            m, c = model.sample(warp[i], cert[i], num=10000)
+            if to_host:
+                m.cpu(), c.cpu()
+                d2h_samples[0] += m.numel() * 4 + c.numel() * c.element_size()
+
+    def run_pairs(inputs, to_host=False):
+        """match() (+ sample()) of the step's pairs: sharded over the ranks from rank 0's tensors, or local sub-batches of P pairs."""
+        if sharded:
+            return sharding.match_sharded(model, *(inputs if rank == 0 else (None, None, None, None)), n_pairs=G, max_batch=P,
+                                          on_batch=lambda w, c: sample_batch(w, c, to_host))
+        outs = []
+        for a in range(0, inputs[0].shape[0], P):
+            w, c = model.match(inputs[0][a:a + P], inputs[1][a:a + P], im_A_high_res=inputs[2][a:a + P], im_B_high_res=inputs[3][a:a + P])
+            sample_batch(w, c, to_host)
+            outs.append((w, c))
+        return outs[0] if len(outs) == 1 else (torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs]))
 
     def step_device():
-        warp, cert = model.match(devt[0], devt[1], im_A_high_res=devt[2], im_B_high_res=devt[3])
-        if not args.no_sample:
-            for i in range(P):
-                model.sample(warp[i], cert[i], num=10000)
-        return warp, cert
+        return run_pairs(devt)
 
     def step_e2e():
+        """The same step from HOST buffers: pinned inputs -> H2D, results (warp, certainty, samples) -> pinned host memory."""
         nonlocal out_host
-        warp, cert = model.match(host[0], host[1], im_A_high_res=host[2], im_B_high_res=host[3])
-        if out_host is None:
-            out_host = (torch.empty(warp.shape, dtype=warp.dtype).pin_memory(), torch.empty(cert.shape, dtype=cert.dtype).pin_memory())
-        out_host[0].copy_(warp, non_blocking=True)
-        out_host[1].copy_(cert, non_blocking=True)
-        d2h = warp.numel() * 4 + cert.numel() * 4
-        if not args.no_sample:
-            for i in range(P):
-                m, c = model.sample(warp[i], cert[i], num=10000)
-                m.cpu(), c.cpu()
-                d2h += m.numel() * 4 + c.numel() * c.element_size()
+        d2h_samples[0] = 0
+        if sharded:
+            if rank == 0:
+                for d, h in zip(devt, host):
+                    d.copy_(h, non_blocking=True)
+            res = run_pairs(devt, to_host=True)
+        else:
+            res = run_pairs(host, to_host=True)          # match() uploads the host tensors itself
+        d2h = d2h_samples[0]
+        if res is not None:
+            warp, cert = res
+            if out_host is None:
+                out_host = (torch.empty(warp.shape, dtype=warp.dtype).pin_memory(), torch.empty(cert.shape, dtype=cert.dtype).pin_memory())
+            out_host[0].copy_(warp, non_blocking=True)
+            out_host[1].copy_(cert, non_blocking=True)
+            d2h += warp.numel() * 4 + cert.numel() * 4
         return d2h
 
     def barrier():
@@ -231,7 +328,7 @@ def run_ours(args):
     ms_prof = timed(step_device, args.steps)
     gemm_prof, stage_prof = eng.gemm_profile, eng.profile
     eng.gemm_profile, eng.profile = None, None
-    h2d = sum(t.numel() * 4 for t in host)
+    h2d = sum(t.numel() * 4 for t in host) if host is not None else 0
     d2h_box = [0]
     for _ in range(2):
         step_e2e()
@@ -269,7 +366,7 @@ def run_ours(args):
         fms = timed(step_device, args.steps)
         ew, ec = golden_errors(fmodel)
         model = main_model
-        fast = {"precision": "fp16 operands / f32 accumulate (the reference's CUDA autocast regime)", "value": P * args.steps / (sum(fms) / 1e3),
+        fast = {"precision": "fp16 operands / f32 accumulate (the reference's CUDA autocast regime)", "value": G * args.steps / (sum(fms) / 1e3),
                 "unit": "pairs/s", "ms_per_step": sum(fms) / args.steps,
                 "parity": {"warp_median": float(np.median(ew)), "warp_p99": float(np.percentile(ew, 99)), "warp_max": float(ew.max()),
                            "certainty_median": float(np.median(ec)), "certainty_p99": float(np.percentile(ec, 99)), "certainty_max": float(ec.max()),
@@ -278,13 +375,24 @@ def run_ours(args):
         fmodel.free_buffers()
         del fmodel
     del mw, dw
+    library = None
+    if rank == 0 and world == 1 and not args.no_library_baseline:
+        model.free_buffers()
+        torch.cuda.empty_cache()
+        try:
+            library = torch_cuda_baseline(dev, steps=min(args.steps, 5), with_sample=not args.no_sample)
+        except Exception as exc:                      # a comparison leg must never take the product's line down
+            library = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     total_ms, total_ms_e2e = sum(ms), sum(ms_e2e)
     if world > 1:
         t = torch.tensor([total_ms, total_ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, total_ms_e2e = t.tolist()
-    pairs = P * world * args.steps
+        tb = torch.tensor([float(h2d), float(d2h_box[0])], device=dev, dtype=torch.float64)      # host<->device bytes of all ranks
+        dist.all_reduce(tb)
+        h2d, d2h_box[0] = int(tb[0].item()), int(tb[1].item())
+    pairs = G * args.steps
     value = pairs / (total_ms / 1e3)
     e2e_value = pairs / (total_ms_e2e / 1e3)
 
@@ -367,22 +475,36 @@ def run_ours(args):
             cpu = {"value": 1.0 / (sum(times) / len(times)), "unit": "pairs/s", "cores": threads, "kind": "port",
                    "sample": f"{len(times)} symmetric pair 560->864 match()" + ("" if args.no_sample else "+sample(10000)") +
                              " through oracle/roma_oracle.py (fp32 restatement of the reference, bit-exact vs it in the build container)"}
+        cfg_name = "configs[1]"
+        if args.global_pairs == 64 and world == 8 and args.model == "outdoor":
+            cfg_name = "configs[2]"
+        elif args.global_pairs == 32 and world == 4 and args.model == "indoor":
+            cfg_name = "configs[3]"
+        workload = (f"roma_{args.model} 560->864, symmetric, full match()" + ("" if args.no_sample else "+sample(10000)") +
+                    (f", batch {G} synthetic pairs sharded over {world} GPU(s) [BASELINE {cfg_name}]" if args.global_pairs else
+                     f", {G} pair(s) per step [BASELINE configs[1] per GPU]"))
+        in_b = 2 * (3 * COARSE * COARSE + 3 * UPSAMPLE * UPSAMPLE) * 4
+        out_b = UPSAMPLE * 2 * UPSAMPLE * 5 * 4
+        wire = sharding.wire_bytes(G, world, in_b, out_b)
         line = {
             "metric": "image-pairs/sec match()+sample() 560->864", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "strong" if args.global_pairs else "weak", "vs_baseline": None,
             "dtype": {"fp16": "f16 operands / f32 accumulate (reference CUDA autocast regime)", "bf16": "bf16 operands / f32 accumulate",
                       "fp32": "f32 (activations f32; GEMM operands as split-f16 pairs hi + 2^-11 lo on tcgen05, f32 accumulate: fp32-class)",
                       "fp32_simt": "f32 (CUDA-core FFMA GEMMs)"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": "roma_outdoor 560->864, symmetric, full match()" + ("" if args.no_sample else "+sample(10000)") +
-                                   " [BASELINE configs[1] per GPU]",
-                       "pairs_per_gpu_per_step": P, "global_pairs_per_step": P * world, "parallelism": f"dp{world} (pairs sharded, no collective)",
+            "config": {"workload": workload,
+                       "pairs_per_match_call": P, "global_pairs_per_step": G,
+                       "parallelism": (f"dp{world}: rank 0 holds the {G} pairs of a step, NCCL scatter of the inputs + gather of warp/certainty inside the "
+                                       f"timed region, {P} pairs per match() call" if sharded else
+                                       (f"dp{world} (every rank on its own resident pairs, no collective)" if world > 1 else "1 GPU")),
+                       "nccl_bytes_per_step": {"scatter": wire[0], "gather": wire[1]} if sharded else None,
                        "precision": args.precision, "weights": "seeded synthetic (no network)",
                        "l2": "256 MiB buffer written between timed steps; per-step activations also exceed the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_box[0],
                     "ms_per_step": total_ms_e2e / args.steps},
-            "parity": parity, "fast_mode": fast,
+            "parity": parity, "fast_mode": fast, "gpu_library_baseline": library,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_kernels": extra, "cpu_baseline": cpu,
             "stage_ms_per_step": {k: round(v, 3) for k, v in sorted(stages.items(), key=lambda kv: -kv[1])},
             "gemm_backends": {k: {"tflops": v[0] / (v[1] / 1e3) / 1e12, "ms_per_step": v[1] / args.steps, "launches_per_step": v[2] / args.steps}
@@ -402,14 +524,26 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_cuda"])
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the stock-PyTorch-CUDA comparison leg (gpu_library_baseline)")
     ap.add_argument("--precision", default=os.environ.get("ROMA_B200_PRECISION", "fp32"), choices=["fp32", "fp32_simt", "fp16", "bf16"])
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the fp16 fast-mode leg reported beside the parity mode")
-    ap.add_argument("--pairs-per-gpu", type=int, default=1)
+    ap.add_argument("--pairs-per-gpu", type=int, default=1, help="pairs per match() call on one GPU")
+    ap.add_argument("--global-pairs", type=int, default=0, help="total pairs per step held by rank 0 and sharded over the GPUs (strong scaling; "
+                    "BASELINE configs[2]: --gpus 8 --global-pairs 64 --pairs-per-gpu 8; configs[3]: --model indoor --gpus 4 --global-pairs 32 --pairs-per-gpu 8)")
+    ap.add_argument("--model", default="outdoor", choices=["outdoor", "indoor"])
+    ap.add_argument("--no-scatter", action="store_true", help="N > 1: every rank on its own resident pairs (no NCCL scatter / gather in the timed region)")
     ap.add_argument("--no-sample", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl == "torch_cuda":
+        import torch
+        if int(os.environ.get("RANK", "0")) == 0:
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            lib = torch_cuda_baseline(torch.device("cuda", torch.cuda.current_device()), steps=args.steps, warmup=max(args.warmup, 2), with_sample=not args.no_sample)
+            print(json.dumps({"impl": "torch_cuda", "metric": "image-pairs/sec match()+sample() 560->864", "unit": "pairs/s", "n_gpus": 1,
+                              "value": lib["fp16_autocast"]["value"], "value_fp32": lib["fp32"]["value"], "gpu_library_baseline": lib}))
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -66,6 +66,8 @@ int romab200_device_ok(void);
  * Row map of the store: NONE; PAD_KEEP (m indexes a zero-padded [*,pad_h,pad_w] grid, border rows are
  * not written); PAD_TO_COMPACT (same, interior rows are written to the un-padded row index);
  * SEGMENT (row m -> (m / seg_in) * seg_out + m % seg_in + seg_off).
+ * Output pitch: the tcgen05 back-end stores tiles with TMA when ldc (and the batch strides) are multiples of 16 bytes; TMA clips at
+ * 16-byte granules, so the pad columns N .. roundup(N, 16 bytes) of a written row receive zeros (columns beyond are untouched).
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
     const void* A; const void* B; void* C;
@@ -176,7 +178,10 @@ typedef struct {
     int32_t algo;   /* 0: 32-wide panels, chain of small launches (no workspace)
                        1: the same as ONE cooperative persistent kernel; workspace >= (batch*ceil(n/32)*1024 + 1)*4 bytes
                        2: 128-wide blocks factored in shared memory with explicit block inverses, all O(n^2) work as K=128
-                          GEMMs; workspace >= batch*ceil(n/128)*65536 bytes (receives the diagonal-block inverses) */
+                          GEMMs; workspace >= batch*ceil(n/128)*65536 bytes (receives the diagonal-block inverses)
+                       3: the schedule of 2 with those GEMMs on the tensor cores (split-fp16 operand pairs, fp32-class; the symmetric
+                          trailing update is an in-place TMA reduce-add); n % 4 == 0, ldw % 8 == 0, stride % 8 == 0; workspace >=
+                          batch * (ceil(n/128)*65536 + 4*max((n+nrhs)*128 + 16384, nrhs*128 + 16384 + 128*ldw)) bytes */
 } rb_gp_solve_args;
 int romab200_gp_solve(const rb_gp_solve_args* args, void* stream);
 /* ---- classifier head -> coarse flow (utils.py:300-322) ------------------------------------------
@@ -212,6 +217,17 @@ typedef struct {
     const float* win_x; const float* win_y;   /* window offsets in normalised coordinates, 2r+1 each */
 } rb_local_corr_args;
 int romab200_local_corr(const rb_local_corr_args* args, void* stream);
+
+/* The fused-local-corr wheel's operator, signature for signature (`local_corr.local_corr`, local_correlation.py:22-35):
+ * out[b, p, k] = sum_c f0[b, p, c] * sample(f1[b], warp[b, p, k, :]), sample = bilinear (mode 0) or nearest (mode 1) lookup at the
+ * normalised (x, y) position, align_corners=False, zero padding (grid_sample semantics); f0 is used as given (the caller pre-scales
+ * by 1/sqrt(C) like `local_corr_wrapper` does).  f0 [B, HW, C] fp32 (pitch ldf0), f1 [B, H, W, C] fp32 channels-last (pitch ldf1),
+ * warp [B, HW, K, 2] fp32 contiguous, out [B, HW, K] fp32 contiguous.  Arbitrary warps: nothing is assumed about a window lattice. */
+typedef struct {
+    const float* f0; const float* f1; int64_t ldf0, ldf1; const float* warp; float* out;
+    int32_t batch, h, w, c, k; int32_t mode;
+} rb_local_corr_warp_args;
+int romab200_local_corr_warp(const rb_local_corr_warp_args* args, void* stream);
 
 /* depthwise 5x5 conv (pad 2) + folded BN + ReLU on channels-last maps (create_block conv1+norm+relu,
  * matcher.py:106-120).  weight [25][ldw] fp32 (tap-major), bias [C] */

@@ -7,7 +7,7 @@ SURVEY.md §8c).  Every function cites the reference file:line it follows.  It e
 the CUDA path in `roma_b200/` can be checked on a box that has no copy of the reference.
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline legs may import it; the
-product package never does (tests/test_layout.py enforces that).
+product package never does (tests/test_host_logic.py::test_layout_product_never_imports_oracle enforces that).
 
 Pinning: the reference has no tensor-level golden vectors, so the oracle is pinned
 against outputs of the *unmodified reference itself*, imported from /root/reference in the build
@@ -34,12 +34,13 @@ REFINER = {16: (128, 7), 8: (64, 3), 4: (32, 2), 2: (16, 0), 1: (6, 0)}   # scal
 SCALES = (16, 8, 4, 2, 1)
 
 
-def pixel_centre_grid(b: int, h: int, w: int) -> torch.Tensor:
-    """[b,2,h,w] normalised pixel-centre coordinates, channel 0 = x (matcher.py:365-377)."""
+def pixel_centre_grid(b: int, h: int, w: int, device="cpu") -> torch.Tensor:
+    """[b,2,h,w] normalised pixel-centre coordinates, channel 0 = x (matcher.py:365-377).  Always built on the CPU (the
+    values the fixtures were pinned with) and then moved: `device` only matters for the stock-PyTorch-CUDA timing leg."""
     ys = torch.linspace(-1 + 1 / h, 1 - 1 / h, h)
     xs = torch.linspace(-1 + 1 / w, 1 - 1 / w, w)
     gy, gx = torch.meshgrid(ys, xs, indexing="ij")
-    return torch.stack((gx, gy))[None].expand(b, 2, h, w)
+    return torch.stack((gx, gy))[None].expand(b, 2, h, w).to(device)
 
 
 class RomaOracle:
@@ -47,9 +48,12 @@ class RomaOracle:
 
     def __init__(self, matcher_weights: Dict[str, torch.Tensor], dinov2_weights: Dict[str, torch.Tensor],
                  coarse_res=560, upsample_res=864, symmetric=True, upsample_preds=True,
-                 attenuate_cert=True, sample_thresh=0.05, sample_mode="threshold_balanced"):
-        self.w = {k: v.float() if v.is_floating_point() else v for k, v in matcher_weights.items()}
-        self.d = {k: v.float() for k, v in dinov2_weights.items()}
+                 attenuate_cert=True, sample_thresh=0.05, sample_mode="threshold_balanced", device="cpu"):
+        # device != "cpu" is the stock-PyTorch-on-GPU timing leg of bench.py (`--impl torch_cuda`): the same torch.nn.functional
+        # graph on cuDNN / cuBLAS / SDPA kernels; every parity check uses the CPU default
+        self.device = torch.device(device)
+        self.w = {k: (v.float() if v.is_floating_point() else v).to(self.device) for k, v in matcher_weights.items()}
+        self.d = {k: v.float().to(self.device) for k, v in dinov2_weights.items()}
         cr = (coarse_res, coarse_res) if isinstance(coarse_res, int) else tuple(coarse_res)
         ur = (upsample_res, upsample_res) if isinstance(upsample_res, int) else upsample_res
         self.h_resized, self.w_resized = cr
@@ -150,13 +154,13 @@ class RomaOracle:
         b, c, h1, w1 = x.shape
         _, _, h2, w2 = y.shape
         w = self.w
-        f = torch.cos(8 * math.pi * F.conv2d(pixel_centre_grid(b, h2, w2),
+        f = torch.cos(8 * math.pi * F.conv2d(pixel_centre_grid(b, h2, w2, x.device),
                                               w["decoder.gps.16.pos_conv.weight"], w["decoder.gps.16.pos_conv.bias"]))
         flat = lambda t: t.flatten(2).transpose(1, 2)
         x, y, f = flat(x.float()), flat(y.float()), flat(f)
         k_yy = self.cos_kernel(y, y)
         k_xy = self.cos_kernel(x, y)
-        noise = 0.1 * torch.eye(h2 * w2)[None]
+        noise = 0.1 * torch.eye(h2 * w2)[None].to(x.device)
         chol = torch.linalg.cholesky(k_yy + noise)
         alpha = torch.cholesky_solve(f, chol, upper=False)
         mu = k_xy @ alpha
@@ -183,7 +187,7 @@ class RomaOracle:
         res = round(math.sqrt(c))
         lin = torch.linspace(-1 + 1 / res, 1 - 1 / res, res)
         gy, gx = torch.meshgrid(lin, lin, indexing="ij")
-        anchors = torch.stack((gx, gy), dim=-1).reshape(c, 2)
+        anchors = torch.stack((gx, gy), dim=-1).reshape(c, 2).to(cls.device)
         p = cls.softmax(dim=1)
         mode = p.max(dim=1).indices
         idx = torch.stack((mode - 1, mode, mode + 1, mode - res, mode + res), dim=1).clamp(0, c - 1)
@@ -201,9 +205,9 @@ class RomaOracle:
         wy = torch.linspace(-2 * r / h, 2 * r / h, 2 * r + 1)
         wx = torch.linspace(-2 * r / w, 2 * r / w, 2 * r + 1)
         oy, ox = torch.meshgrid(wy, wx, indexing="ij")
-        window = torch.stack((ox, oy), dim=-1).reshape(1, k, 2)
+        window = torch.stack((ox, oy), dim=-1).reshape(1, k, 2).to(f0.device)
         flow = flow.permute(0, 2, 3, 1)
-        corr = torch.empty(b, k, h, w)
+        corr = torch.empty(b, k, h, w, device=f0.device)
         for i in range(b):
             coords = (flow[i, :, :, None] + window[:, None, None]).reshape(1, h, w * k, 2)
             samp = F.grid_sample(f1[i:i + 1], coords, padding_mode="zeros", align_corners=False,
@@ -217,7 +221,7 @@ class RomaOracle:
         emb_dim, r = REFINER[s]
         p = f"decoder.conv_refiner.{s}"
         x_hat = F.grid_sample(y, flow.permute(0, 2, 3, 1), align_corners=False, mode="bilinear")
-        disp = flow - pixel_centre_grid(b, hs, ws)
+        disp = flow - pixel_centre_grid(b, hs, ws, flow.device)
         emb = F.conv2d(40 / 32 * scale_factor * disp, self.w[f"{p}.disp_emb.weight"], self.w[f"{p}.disp_emb.bias"])
         parts = [x, x_hat, emb]
         if r:
@@ -251,7 +255,7 @@ class RomaOracle:
         b = f1[1].shape[0]
         tag = "up" if upsample else "lo"
         if not upsample:
-            flow, certainty = pixel_centre_grid(b, *sizes[16]), 0.0
+            flow, certainty = pixel_centre_grid(b, *sizes[16], device=f1[1].device), 0.0
         else:
             flow = F.interpolate(flow, size=sizes[8], align_corners=False, mode="bilinear")
             certainty = F.interpolate(certainty, size=sizes[8], align_corners=False, mode="bilinear")
@@ -313,7 +317,7 @@ class RomaOracle:
         flow = corresps[1]["flow"].permute(0, 2, 3, 1)
         cert = (corresps[1]["certainty"] - low).sigmoid()
         self._rec("final.flow", flow), self._rec("final.logit", corresps[1]["certainty"] - low)
-        grid = pixel_centre_grid(b, hs, ws).permute(0, 2, 3, 1)
+        grid = pixel_centre_grid(b, hs, ws, flow.device).permute(0, 2, 3, 1)
         if (flow.abs() > 1).any():
             wrong = (flow.abs() > 1).sum(dim=-1) > 0
             cert[wrong[:, None]] = 0

@@ -101,6 +101,77 @@ def _stream():
 
 launch_count = 0      # number of C-ABI calls made (bench.py reports kernel launches from it)
 
+# ---- argument validation: the C ABI takes raw pointers, so a tensor of the wrong dtype / device / layout would be silent garbage.
+# For every struct: tensor field -> the field that carries its dtype code (or a fixed torch dtype).
+_CODE_DTYPE = {RB_F32: torch.float32, RB_F16: torch.float16, RB_BF16: torch.bfloat16, RB_F16S: torch.float16}
+_F32 = torch.float32
+_FIELD_DTYPES = {
+    "rb_gemm_args": {"A": "dtype_ab", "B": "dtype_ab", "A_lo": torch.float16, "B_lo": torch.float16, "C": "dtype_c", "C_lo": torch.float16,
+                     "R": "dtype_r", "bias": _F32, "col_scale": _F32, "norm_a": _F32, "norm_b": _F32},
+    "rb_layernorm_args": {"x": "dtype_x", "y": "dtype_y", "y_lo": torch.float16, "gamma": _F32, "beta": _F32},
+    "rb_softmax_args": {"s": "dtype", "out_hi": torch.float16, "out_lo": torch.float16},
+    "rb_flash_attn_args": {"qkv": "dtype", "out": "dtype", "qkv_lo": torch.float16, "out_lo": torch.float16},
+    "rb_rownorm_args": {"x": "dtype", "out": _F32},
+    "rb_copy2d_args": {"src": "dtype_src", "dst": "dtype_dst", "row_scale": _F32},
+    "rb_split_pair_args": {"x": _F32, "hi": torch.float16, "lo": torch.float16, "row_norm": _F32},
+    "rb_conv_first_args": {"image": _F32, "out": "dtype_out", "out_lo": torch.float16, "weight": _F32, "bias": _F32},
+    "rb_maxpool_args": {"in": "dtype", "out": "dtype", "in_lo": torch.float16, "out_lo": torch.float16},
+    "rb_im2col_args": {"image": _F32, "out": "dtype_out"},
+    "rb_tokens_args": {"patch": _F32, "cls": _F32, "pos": _F32, "tokens": _F32},
+    "rb_gp_solve_args": {"W": _F32},
+    "rb_cls_args": {"logits": "dtype", "state": _F32},
+    "rb_refiner_prologue_args": {"feat": "dtype", "state": _F32, "d": "dtype", "emb_weight": _F32, "emb_bias": _F32, "grid_x": _F32, "grid_y": _F32,
+                                 "win_x": _F32, "win_y": _F32},
+    "rb_local_corr_args": {"f0": "dtype_f", "f1": "dtype_f", "flow": _F32, "out": "dtype_out", "win_x": _F32, "win_y": _F32},
+    "rb_local_corr_warp_args": {"f0": _F32, "f1": _F32, "warp": _F32, "out": _F32},
+    "rb_dwconv_args": {"in": "dtype", "weight": _F32, "bias": _F32, "out_lo": torch.float16},
+    "rb_refiner_block_small_args": {"in": "dtype", "out": "dtype", "dw_weight": _F32, "dw_bias": _F32},
+    "rb_refiner_block_c144_args": {"in": "dtype", "out": "dtype", "dw_weight": _F32, "dw_bias": _F32, "pw_weight": "dtype", "pw_bias": _F32},
+    "rb_refiner_tail_args": {"d": "dtype", "weight": _F32, "bias": _F32, "state": _F32, "delta_out": _F32},
+    "rb_resize_args": {"in": _F32, "out": _F32},
+    "rb_match_epilogue_args": {"state": _F32, "coarse_state": _F32, "warp": _F32, "cert": _F32, "grid_x": _F32, "grid_y": _F32},
+    "rb_kde_args": {"x": _F32, "density": _F32},
+    "rb_sample_args": {"weights": _F32, "keys": _F32},
+}
+
+
+def _gemm_min_elems(kw):
+    """(field, minimum number of elements) of the GEMM operands for the given geometry."""
+    b0, b1 = kw.get("batch0", 1) or 1, kw.get("batch1", 1) or 1
+    M, N, K, nt = kw["M"], kw["N"], kw["K"], kw.get("ntaps", 1) or 1
+    offa = (b0 - 1) * kw.get("sa0", 0) + (b1 - 1) * kw.get("sa1", 0)
+    offb = (b0 - 1) * kw.get("sb0", 0) + (b1 - 1) * kw.get("sb1", 0)
+    offc = (b0 - 1) * kw.get("sc0", 0) + (b1 - 1) * kw.get("sc1", 0)
+    a = offa + ((kw.get("a_rows") or M) - 1) * kw["lda"] + K // nt
+    b = offb + ((K - 1) * kw["ldb"] + N if kw.get("trans_b", 0) else (N - 1) * kw["ldb"] + K)
+    rows_out = M
+    if kw.get("rowmap", 0) == ROWMAP_PAD_TO_COMPACT:
+        rows_out = M // (kw["pad_h"] * kw["pad_w"]) * (kw["pad_h"] - 2) * (kw["pad_w"] - 2)
+    elif kw.get("rowmap", 0) == ROWMAP_SEGMENT:
+        rows_out = (M + kw["seg_in"] - 1) // kw["seg_in"] * kw["seg_out"] + kw.get("seg_off", 0)
+    c = offc + (rows_out - 1) * kw["ldc"] + N
+    return {"A": a, "A_lo": a, "B": b, "B_lo": b, "C": c, "C_lo": c}
+
+
+def _validate(fn_name, struct_name, kw):
+    table = _FIELD_DTYPES.get(struct_name, {})
+    cur = torch.cuda.current_device() if torch.cuda.is_available() else None
+    mins = _gemm_min_elems(kw) if struct_name == "rb_gemm_args" else {}
+    for k, v in kw.items():
+        if not isinstance(v, torch.Tensor):
+            continue
+        if not v.is_cuda or (cur is not None and v.device.index != cur):
+            raise RuntimeError(f"{fn_name}: argument `{k}` lives on {v.device}, expected the current CUDA device cuda:{cur}")
+        if not v.is_contiguous():
+            raise RuntimeError(f"{fn_name}: argument `{k}` is not contiguous (shape {tuple(v.shape)}, strides {v.stride()})")
+        want = table.get(k)
+        if isinstance(want, str):
+            want = _CODE_DTYPE.get(kw.get(want))
+        if want is not None and v.dtype != want:
+            raise RuntimeError(f"{fn_name}: argument `{k}` has dtype {v.dtype}, the call describes it as {want}")
+        if k in mins and v.numel() < mins[k]:
+            raise RuntimeError(f"{fn_name}: argument `{k}` holds {v.numel()} elements, the described geometry needs {mins[k]}")
+
 
 def call(fn_name: str, struct_name: str, **kw) -> None:
     """Fill `struct_name` from keyword arguments (tensors become device pointers) and call `fn_name`."""
@@ -108,9 +179,11 @@ def call(fn_name: str, struct_name: str, **kw) -> None:
     lib = load_library()
     args = STRUCTS[struct_name]()
     valid = {f for f, _ in STRUCT_FIELDS[struct_name]}
-    for k, v in kw.items():
+    for k in kw:
         if k not in valid:
             raise TypeError(f"{struct_name} has no field {k}")
+    _validate(fn_name, struct_name, kw)
+    for k, v in kw.items():
         if isinstance(v, torch.Tensor) or v is None:
             setattr(args, k, _ptr(v))
         elif isinstance(v, (list, tuple)):

@@ -161,5 +161,6 @@ int gemm_simt(const rb_gemm_args* a, cudaStream_t stream, int lower_only = 0);
 int gemm_tc(const rb_gemm_args* a, cudaStream_t stream);
 int dwconv_tma(const rb_dwconv_args* a, cudaStream_t stream);     // dwconv_tma.cu: TMA-fed persistent depthwise kernel (16-bit maps)
 Epilogue make_epilogue(const rb_gemm_args* a);
+int split_f16s_batched(const float* x, void* hi, void* lo, int64_t rows, int cols, int64_t ldx, int64_t ldd, int batch, int64_t sx, int64_t sd, cudaStream_t st);
 
 }  // namespace rb

@@ -279,6 +279,22 @@ __global__ void __launch_bounds__(256) split_f16s_vec_kernel(const float* __rest
         *reinterpret_cast<uint2*>(lo + r * ldd + c) = *reinterpret_cast<uint2*>(l);
     }
 }
+// batched variant (blockIdx.y = matrix): used by the tensor-core GP solve for its strided panels
+__global__ void __launch_bounds__(256) split_f16s_batched_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t rows, int cols4,
+                                                                 int64_t ldx, int64_t ldd, int64_t sx, int64_t sd) {
+    rb::pdl_wait();
+    x += blockIdx.y * sx; hi += blockIdx.y * sd; lo += blockIdx.y * sd;
+    const int64_t total = rows * cols4;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / cols4; const int c = (int)(idx - r * cols4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+        __half h[4], l[4];
+        split_f16s(v.x, h[0], l[0]); split_f16s(v.y, h[1], l[1]); split_f16s(v.z, h[2], l[2]); split_f16s(v.w, h[3], l[3]);
+        *reinterpret_cast<uint2*>(hi + r * ldd + c) = *reinterpret_cast<uint2*>(h);
+        *reinterpret_cast<uint2*>(lo + r * ldd + c) = *reinterpret_cast<uint2*>(l);
+    }
+}
+
 __global__ void split_f16s_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t rows, int cols,
                                   int64_t ldx, int64_t ldd, const float* __restrict__ norm) {
     rb::pdl_wait();
@@ -345,6 +361,17 @@ __global__ void transpose_kernel(const T* __restrict__ src, T* __restrict__ dst,
 static inline int grid_for(int64_t total, int block, int cap = 148 * 32) {
     int64_t g = (total + block - 1) / block;
     return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// fp32 [batch][rows, cols] (pitch ldx, matrix stride sx) -> RB_F16S planes [batch][rows, ldd] (matrix stride sd); cols % 4 == 0,
+// 16-byte aligned rows
+int split_f16s_batched(const float* x, void* hi, void* lo, int64_t rows, int cols, int64_t ldx, int64_t ldd, int batch, int64_t sx, int64_t sd, cudaStream_t st) {
+    RB_REQUIRE(cols % 4 == 0 && ldx % 4 == 0 && ldd % 4 == 0 && sx % 4 == 0 && sd % 4 == 0 && ((uintptr_t)x) % 16 == 0 && ((uintptr_t)hi) % 8 == 0 && ((uintptr_t)lo) % 8 == 0,
+               "split_f16s_batched: alignment");
+    RB_REQUIRE(batch > 0 && batch <= 65535 && rows > 0, "split_f16s_batched: bad shape");
+    dim3 grid(grid_for(rows * (cols / 4), 256, 148 * 8), batch);
+    rb::launch_pdl(split_f16s_batched_kernel, grid, dim3(256), 0, st, x, (__half*)hi, (__half*)lo, rows, cols / 4, ldx, ldd, sx, sd);
+    return check_launch("split_f16s_batched");
 }
 
 }  // namespace rb

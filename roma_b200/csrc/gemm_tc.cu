@@ -294,6 +294,10 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
     #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
+            if (nb + 32 > nlim) {       // the N tail: TMA clips at 16-byte granules, so the pad columns up to the next granule receive zeros
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j >= nlim) v[j] = 0.f;
+            }
             uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
             const int row0 = m0 + q * 32;
             if (e.dtype_c == RB_F16 || e.dtype_c == RB_BF16) {

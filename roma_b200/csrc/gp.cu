@@ -602,6 +602,8 @@ __global__ void __launch_bounds__(CB_THREADS) chol_block128_kernel(float* __rest
     CBCLK(12)
 }
 
+struct Split2 { __half* hi; __half* lo; };
+
 static int plain_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int trans_b, float* C, int64_t ldc, int M, int N, int K,
                       int batch, int64_t sa, int64_t sb, int64_t sc, cudaStream_t st) {
     rb_gemm_args g = {};
@@ -652,6 +654,83 @@ static int gp_solve_block128(const rb_gp_solve_args* a, cudaStream_t st) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// algo 3: the schedule of algo 2 with every O(n^2 * 128) product on the tensor cores.  The panels are converted to RB_F16S pairs
+// (split_f16s_batched) and contracted by the split-fp16 tcgen05 GEMM (fp32-class: K = 128 means 8 accumulator updates); the
+// symmetric trailing update and the back-substitution update are in-place fp32 reduce-adds of the TMA-store epilogue.  Nothing
+// aliases any more: the GEMMs read the scratch pairs and write the fp32 workspace.
+//   workspace = [batch * nblk * 128 * 128 fp32 block inverses | scratch pairs], see gp_tc_workspace_bytes().
+// ---------------------------------------------------------------------------------------------------------------------------
+static int64_t gp_tc_scratch_halves(int n, int nrhs, int64_t ldw) {       // fp16 elements per problem and plane
+    const int64_t fwd = (int64_t)(n + nrhs) * BB + BB * BB;               // panel rows + inverse block
+    const int64_t bwd = (int64_t)nrhs * BB + BB * BB + BB * ldw;          // Y block + inverse block + L rows
+    return fwd > bwd ? fwd : bwd;
+}
+
+static int tc_gemm(const Split2& A, int64_t lda, const Split2& B, int64_t ldb, int trans_b, float* C, int64_t ldc, int M, int N, int K, int batch,
+                   int64_t sa, int64_t sb, int64_t sc, float alpha, bool accumulate, cudaStream_t st) {
+    rb_gemm_args g = {};
+    g.A = A.hi; g.A_lo = A.lo; g.B = B.hi; g.B_lo = B.lo; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    g.dtype_ab = RB_F16S; g.dtype_c = RB_F32; g.trans_b = trans_b;
+    g.batch0 = batch; g.batch1 = 1; g.sa0 = sa; g.sb0 = sb; g.sc0 = sc;
+    g.ntaps = 1; g.alpha = alpha;
+    if (accumulate) { g.R = C; g.ldr = ldc; g.dtype_r = RB_F32; g.sr0 = sc; }
+    return gemm_tc(&g, st);
+}
+
+static int gp_solve_tc(const rb_gp_solve_args* a, cudaStream_t st) {
+    const int n = a->n, total = a->n + a->nrhs, nblk = (n + BB - 1) / BB;
+    const int64_t ws_stride = (int64_t)nblk * BB * BB;
+    float* W = a->W;
+    float* ws = (float*)a->workspace;
+    const int64_t sh = gp_tc_scratch_halves(n, a->nrhs, a->ldw);          // plane stride between problems
+    __half* s_hi = reinterpret_cast<__half*>(ws + (int64_t)a->batch * ws_stride);
+    __half* s_lo = s_hi + (int64_t)a->batch * sh;
+    static bool configured[64] = {};
+    const int dev = current_device() & 63;
+    const size_t smem = (size_t)CB_SMEM_FLOATS * sizeof(float);
+    if (!configured[dev]) {
+        RB_REQUIRE(cudaFuncSetAttribute(chol_block128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
+                   "gp_solve: cannot reserve %zu bytes of shared memory", smem);
+        configured[dev] = true;
+    }
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k = kb * BB, bs = n - k < BB ? n - k : BB;
+        rb::launch_pdl(chol_block128_kernel, dim3(a->batch), dim3(CB_THREADS), smem, st, W, ws, a->ldw, a->stride, ws_stride, k, kb, bs);
+        if (check_launch("chol_block128")) return 1;
+        const int below = total - (k + bs);
+        if (below <= 0) continue;
+        float* P = W + (int64_t)(k + bs) * a->ldw + k;                   // A21 (and the F^T rows)  ->  P = A21 L11^-T
+        const Split2 sP{s_hi, s_lo}, sInv{s_hi + (int64_t)total * BB, s_lo + (int64_t)total * BB};
+        if (split_f16s_batched(P, sP.hi, sP.lo, below, bs, a->ldw, BB, a->batch, a->stride, sh, st)) return 1;
+        if (split_f16s_batched(ws + (int64_t)kb * BB * BB, sInv.hi, sInv.lo, bs, bs, BB, BB, a->batch, ws_stride, sh, st)) return 1;
+        if (tc_gemm(sP, BB, sInv, BB, 0, P, a->ldw, below, bs, bs, a->batch, sh, sh, a->stride, 1.0f, false, st)) return 1;
+        const int nt = n - (k + bs);
+        if (nt > 0) {
+            if (split_f16s_batched(P, sP.hi, sP.lo, below, bs, a->ldw, BB, a->batch, a->stride, sh, st)) return 1;
+            float* Tm = W + (int64_t)(k + bs) * a->ldw + (k + bs);        // trailing matrix (+ F^T rows) -= P P^T  (first nt rows of P as B)
+            if (tc_gemm(sP, BB, sP, BB, 0, Tm, a->ldw, below, nt, bs, a->batch, sh, sh, a->stride, -1.0f, true, st)) return 1;
+        }
+    }
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int k = kb * BB, bs = n - k < BB ? n - k : BB;
+        float* Y = W + (int64_t)n * a->ldw + k;                            // RHS block  ->  X = Y L11^-1
+        const Split2 sY{s_hi, s_lo}, sInv{s_hi + (int64_t)a->nrhs * BB, s_lo + (int64_t)a->nrhs * BB};
+        const Split2 sL{sInv.hi + BB * BB, sInv.lo + BB * BB};
+        if (split_f16s_batched(Y, sY.hi, sY.lo, a->nrhs, bs, a->ldw, BB, a->batch, a->stride, sh, st)) return 1;
+        if (split_f16s_batched(ws + (int64_t)kb * BB * BB, sInv.hi, sInv.lo, bs, bs, BB, BB, a->batch, ws_stride, sh, st)) return 1;
+        if (tc_gemm(sY, BB, sInv, BB, 1, Y, a->ldw, a->nrhs, bs, bs, a->batch, sh, sh, a->stride, 1.0f, false, st)) return 1;
+        if (k > 0) {
+            float* Lr = W + (int64_t)k * a->ldw;                           // L[k:k+bs, 0:k] as the [K, N] operand
+            float* Y0 = W + (int64_t)n * a->ldw;
+            if (split_f16s_batched(Y, sY.hi, sY.lo, a->nrhs, bs, a->ldw, BB, a->batch, a->stride, sh, st)) return 1;
+            if (split_f16s_batched(Lr, sL.hi, sL.lo, bs, k, a->ldw, a->ldw, a->batch, a->stride, sh, st)) return 1;
+            if (tc_gemm(sY, BB, sL, a->ldw, 1, Y0, a->ldw, a->nrhs, k, bs, a->batch, sh, sh, a->stride, -1.0f, true, st)) return 1;
+        }
+    }
+    return 0;
+}
+
 }  // namespace rb
 
 using namespace rb;
@@ -664,6 +743,13 @@ extern "C" int romab200_gp_solve(const rb_gp_solve_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->n > 0 && a->nrhs > 0 && a->batch > 0 && a->ldw >= a->n, "gp_solve: bad shape n=%d nrhs=%d batch=%d", a->n, a->nrhs, a->batch);
     RB_REQUIRE(a->batch <= 65535, "gp_solve: batch too large");
+    if (a->workspace && a->algo == 3) {
+        const int64_t nblk128 = (a->n + BB - 1) / BB;
+        RB_REQUIRE(a->ldw % 8 == 0 && a->stride % 8 == 0 && a->n % 4 == 0 && ((uintptr_t)a->W) % 16 == 0 && ((uintptr_t)a->workspace) % 16 == 0, "gp_solve: alignment (algo 3)");
+        const int64_t need = (int64_t)a->batch * (nblk128 * BB * BB * 4 + 4 * gp_tc_scratch_halves(a->n, a->nrhs, a->ldw));
+        RB_REQUIRE(a->workspace_bytes >= need, "gp_solve: workspace too small for algo 3 (%lld < %lld bytes)", (long long)a->workspace_bytes, (long long)need);
+        return gp_solve_tc(a, st);
+    }
     if (a->workspace && a->algo == 2) {
         const int64_t nblk128 = (a->n + BB - 1) / BB;
         RB_REQUIRE(a->ldw % 4 == 0 && ((uintptr_t)a->W) % 16 == 0 && ((uintptr_t)a->workspace) % 16 == 0, "gp_solve: alignment");

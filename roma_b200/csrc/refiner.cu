@@ -304,6 +304,50 @@ __global__ void __launch_bounds__(128) local_corr_kernel(const LocalCorrParams p
                               (TO*)p.out + pix * p.ldo, lane);
 }
 
+
+// --------------------------------------------------------------------------------------------------
+// Generic local correlation with the wheel's interface (romab200_local_corr_warp): one warp per (b, p); for every k the
+// (up to) four corner rows of f1 are blended lane-wise over the channels and dotted with f0 — any warp, no lattice assumed.
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) local_corr_warp_kernel(const float* __restrict__ f0, const float* __restrict__ f1, int64_t ldf0, int64_t ldf1,
+                                                              const float* __restrict__ warp, float* __restrict__ out, int B, int H, int W, int C, int K, int mode) {
+    rb::pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int64_t pix = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t hw = (int64_t)H * W;
+    if (pix >= (int64_t)B * hw) return;
+    const int b = (int)(pix / hw);
+    const float* q = f0 + pix * ldf0;
+    const float* img = f1 + (int64_t)b * hw * ldf1;
+    for (int k = 0; k < K; ++k) {
+        const float gx = warp[(pix * K + k) * 2], gy = warp[(pix * K + k) * 2 + 1];
+        const float ix = ((gx + 1.f) * W - 1.f) * 0.5f, iy = ((gy + 1.f) * H - 1.f) * 0.5f;
+        int xs[4], ys[4]; float ws[4]; int n = 0;
+        if (mode == 1) {                                  // nearest: round half to even like ATen's grid_sampler
+            xs[0] = (int)nearbyintf(ix); ys[0] = (int)nearbyintf(iy); ws[0] = 1.f; n = 1;
+        } else {
+            const float fx0 = floorf(ix), fy0 = floorf(iy);
+            const int x0 = (int)fx0, y0 = (int)fy0;
+            const float ax = ix - fx0, ay = iy - fy0;
+            xs[0] = x0; ys[0] = y0; ws[0] = (1.f - ax) * (1.f - ay);
+            xs[1] = x0 + 1; ys[1] = y0; ws[1] = ax * (1.f - ay);
+            xs[2] = x0; ys[2] = y0 + 1; ws[2] = (1.f - ax) * ay;
+            xs[3] = x0 + 1; ys[3] = y0 + 1; ws[3] = ax * ay;
+            n = 4;
+        }
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            float v = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (t < n && xs[t] >= 0 && xs[t] < W && ys[t] >= 0 && ys[t] < H) v = fmaf(ws[t], img[((int64_t)ys[t] * W + xs[t]) * ldf1 + c], v);
+            acc = fmaf(q[c], v, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[pix * K + k] = acc;
+    }
+}
+
 // --------------------------------------------------------------------------------------------------
 // depthwise 5x5 + folded BN + ReLU, channels-last.  Block = 8 output rows x 16 output columns x 32 channels;
 // the (8+4)x(16+4)x32 input tile is staged in shared memory as fp32; each thread owns one channel of one
@@ -814,6 +858,18 @@ extern "C" int romab200_local_corr(const rb_local_corr_args* a, void* stream) {
 #undef BYR
 #undef LAUNCH
     return check_launch("local_corr");
+}
+
+extern "C" int romab200_local_corr_warp(const rb_local_corr_warp_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_REQUIRE(a->f0 && a->f1 && a->warp && a->out && a->batch > 0 && a->h > 0 && a->w > 0 && a->c > 0 && a->k > 0, "local_corr_warp: bad arguments");
+    RB_REQUIRE(a->mode == 0 || a->mode == 1, "local_corr_warp: mode must be 0 (bilinear) or 1 (nearest)");
+    RB_REQUIRE(a->ldf0 >= a->c && a->ldf1 >= a->c, "local_corr_warp: pitches smaller than the channel count");
+    const int64_t pixels = (int64_t)a->batch * a->h * a->w;
+    RB_REQUIRE((pixels + 7) / 8 < (1ll << 31), "local_corr_warp: grid too large");
+    rb::launch_pdl(local_corr_warp_kernel, dim3((unsigned)((pixels + 7) / 8)), dim3(256), 0, st, a->f0, a->f1, a->ldf0, a->ldf1, a->warp, a->out, a->batch, a->h, a->w,
+                   a->c, a->k, a->mode);
+    return check_launch("local_corr_warp");
 }
 
 extern "C" int romab200_dwconv5x5_relu(const rb_dwconv_args* a, void* stream) {

@@ -59,9 +59,9 @@ class Engine:
         self._const: Dict[tuple, torch.Tensor] = {}
         self.debug: Optional[dict] = None        # set to {} to keep stage tensors (tests)
         self.use_flash_attn = True               # fused tcgen05 attention in the 16-bit modes (else QK^T / softmax / PV GEMMs)
-        self.gp_algo = 2                         # 2: 128-wide blocks factored in shared memory + explicit block inverses, the rest
-                                                 # K=128 GEMMs (13 dependent steps); 0: 32-wide launch chain (50 steps);
-                                                 # 1: one cooperative persistent kernel.  Timings in DESIGN.md.
+        self.gp_algo = 2 if precision == "fp32_simt" else 3   # 3: 128-wide blocks factored in shared memory + explicit block inverses, the
+                                                 # K=128 GEMMs (13 dependent steps) on the tensor cores as split-fp16 pairs; 2: the same with
+                                                 # CUDA-core GEMMs; 0: 32-wide launch chain (50 steps); 1: one cooperative persistent kernel.
         self.overlap_cnn = True                  # VGG/proj branch on a side stream, overlapping ViT / GP / decoder
         self.gp_tensor_core = True               # all-pairs CosKernel on tcgen05 (split-fp16 operands) in the 16-bit modes
         self.fused_c144 = True                   # stride-2 refiner blocks as one fused DW + tcgen05-PW kernel
@@ -152,8 +152,8 @@ class Engine:
     def gemm(self, A, B, C, M, N, K, lda, ldb, ldc, dtype_ab=None, dtype_c=None, **kw):
         args = dict(M=M, N=N, K=K, lda=lda, ldb=ldb, ldc=ldc, batch0=1, batch1=1, ntaps=1, alpha=1.0)
         args.update(kw)
-        if self.split and dtype_ab is None:
-            # parity mode: operands as RB_F16S pairs.  Activations that no kernel wrote in that format are split here.
+        if (self.split and dtype_ab is None) or isinstance(A, Split):
+            # parity mode (and the GP block of every tensor-core mode): operands as RB_F16S pairs.  Activations that no kernel wrote in that format are split here.
             if not isinstance(A, Split):
                 assert args["batch0"] * args["batch1"] == 1 and lda % 8 == 0, "batched fp32 operands are split by the caller"
                 A = self.split_pair(A, args.get("a_rows") or M, K // args["ntaps"], lda)
@@ -356,9 +356,10 @@ class Engine:
         Wk = self.buf("gp.work", (E, n + nrhs, ldw), dtype=torch.float32)
         stride_w = (n + nrhs) * ldw
         # K_yy + sigma*I for every image (its own features): exp((cos-1)/T)   (matcher.py:191-200, 298, 301)
-        tc_kernel = self.dtype != torch.float32 and self.gp_tensor_core
+        gp_split = self.split or (self.dtype != torch.float32 and self.gp_tensor_core)     # GP contractions as split-fp16 pairs (fp32-class)
+        tc_kernel = False                 # (the K' = 3K operand trick of round 1 is superseded by the split back-end)
         xs = None
-        if self.split:
+        if gp_split:
             # all-pairs CosKernel on tcgen05 with fp32-class accuracy: the L2-normalised rows as an RB_F16S pair
             with self.stage("  gp.split"):
                 xs = self.split_pair(p16, E * n, cf, cf, name="gp.xs", row_norm=norms)
@@ -371,7 +372,7 @@ class Engine:
                 call("romab200_split_f16x3", "rb_split_args", x=p16, dst=xa, rows=E * n, cols=cf, ldx=cf, ldd=3 * cf, row_norm=norms, layout_b=0)
                 call("romab200_split_f16x3", "rb_split_args", x=p16, dst=xb, rows=E * n, cols=cf, ldx=cf, ldd=3 * cf, row_norm=norms, layout_b=1)
         with self.stage("  gp.kyy"):
-            if self.split:
+            if gp_split:
                 self.gp_kernel_matrix_split(xs, xs, norms, norms, Wk, n, cf, ldw, batch=E, sa=n * cf, sb=n * cf, sc=stride_w,
                                             sna=n, snb=n, diag=arch.GP_SIGMA_NOISE)
             elif tc_kernel:
@@ -386,6 +387,8 @@ class Engine:
         with self.stage("  gp.solve"):
             # algo 2: 128-wide blocks factored in shared memory + explicit block inverses, everything else K=128 GEMMs
             ws_bytes = max((E * ((n + 31) // 32) * 1024 + 1) * 4, E * ((n + 127) // 128) * 65536)
+            if self.gp_algo == 3:
+                ws_bytes = E * (((n + 127) // 128) * 65536 + 4 * max((n + nrhs) * 128 + 16384, nrhs * 128 + 16384 + 128 * ldw))
             ws = self.buf("gp.solve_ws", (ws_bytes // 4,), dtype=torch.float32)
             call("romab200_gp_solve", "rb_gp_solve_args", W=Wk, n=n, nrhs=nrhs, batch=E, ldw=ldw, stride=stride_w,
                  workspace=ws if self.gp_algo else None, workspace_bytes=ws_bytes if self.gp_algo else 0, algo=self.gp_algo)
@@ -394,7 +397,7 @@ class Engine:
         tokens = self.buf("dec.tokens_in", (D * n, dim))
         es = tokens.element_size()
         halves = [(0, b, b)] if D == b else [(0, b, b), (b, b, 0)]     # (first item, count, first support image)
-        if self.split:
+        if gp_split:
             kxy = self.sbuf("gp.kxy", (D, n, ldw))
             alpha = self.sbuf("gp.alpha", (E, nrhs, ldw))
             with self.stage("  gp.kxy+mu"):

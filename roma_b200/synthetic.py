@@ -87,17 +87,19 @@ def make_weights(seed: int = 0):
     return make_matcher_weights(seed), make_dinov2_weights(seed)
 
 
-def make_pair(batch: int, coarse: int, upsample: int | None, seed: int = 1):
+def make_pair(batch: int, coarse, upsample, seed: int = 1):
     """Synthetic N(0,1) image tensors, the distribution the reference's own timing tests use
-    (`tests/test_roma_upsample_inference_time.py:9-12`): (A, B, A_high, B_high)."""
+    (`tests/test_roma_upsample_inference_time.py:9-12`): (A, B, A_high, B_high).  Resolutions are ints (square) or (h, w)."""
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
-    a = torch.randn(batch, 3, coarse, coarse, generator=g)
-    b = torch.randn(batch, 3, coarse, coarse, generator=g)
+    ch, cw = (coarse, coarse) if isinstance(coarse, int) else coarse
+    a = torch.randn(batch, 3, ch, cw, generator=g)
+    b = torch.randn(batch, 3, ch, cw, generator=g)
     if upsample is None:
         return a, b, None, None
-    ah = torch.randn(batch, 3, upsample, upsample, generator=g)
-    bh = torch.randn(batch, 3, upsample, upsample, generator=g)
+    uh, uw = (upsample, upsample) if isinstance(upsample, int) else upsample
+    ah = torch.randn(batch, 3, uh, uw, generator=g)
+    bh = torch.randn(batch, 3, uh, uw, generator=g)
     return a, b, ah, bh
 
 

@@ -61,7 +61,11 @@ def run(name, coarse, up, symmetric=True, upsample_preds=True, batch=1, seed=1, 
     out["certainty"] = cert[:, ::step, ::step].numpy()
     out["warp_checksum"] = checksum(warp)
     out["certainty_checksum"] = checksum(cert)
-    out["meta"] = np.array([coarse, up or 0, int(symmetric), int(upsample_preds), batch, seed, step])
+    if isinstance(coarse, tuple):          # rectangular resolutions: (h, w) pairs
+        out["res"] = np.array([*coarse, *(up or (0, 0))])
+        out["meta"] = np.array([0, 0, int(symmetric), int(upsample_preds), batch, seed, step])
+    else:
+        out["meta"] = np.array([coarse, up or 0, int(symmetric), int(upsample_preds), batch, seed, step])
     if name == "small_sym_up":
         torch.manual_seed(123)
         m, c = model.sample(warp[0], cert[0], num=500)
@@ -77,5 +81,5 @@ if __name__ == "__main__":
     run("small_sym_noup", 112, None, upsample_preds=False, hooks=False)
     run("small_b2_sym_up", 112, 168, batch=2, seed=7, hooks=False)
     run("small_pil_sym_up", 112, 168, pil=True, hooks=False, seed=3)
-    run("rect_sym_up", (112, 168), (168, 252), hooks=False, seed=5) if False else None
+    run("rect_sym_up", (112, 168), (168, 224), hooks=False, seed=5)
     run("full_sym_up", 560, 864, step=8, hooks=False)

@@ -53,6 +53,23 @@ def test_match_small_vs_reference_golden(weights, name, backend):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
+def test_match_rectangular_vs_reference_golden(weights, backend):
+    """Non-square resolutions (112 x 168 -> 168 x 224) against the unmodified reference."""
+    from roma_b200 import model_zoo, roma_outdoor
+    g = load_golden("rect_sym_up")
+    ch, cw, uh, uw = (int(v) for v in g["res"])
+    model_zoo.fp32_backend = backend
+    try:
+        model = roma_outdoor("cuda", weights=weights[0], dinov2_weights=weights[1], coarse_res=(ch, cw), upsample_res=(uh, uw), amp_dtype=torch.float32)
+    finally:
+        model_zoo.fp32_backend = None
+    A, B, Ah, Bh = synthetic.make_pair(1, (ch, cw), (uh, uw), int(g["meta"][5]))
+    warp, cert = model.match(A.cuda(), B.cuda(), im_A_high_res=Ah.cuda(), im_B_high_res=Bh.cuda())
+    ew, ec = report(f"rect {backend}", warp, cert, g)
+    assert ew <= TOL and ec <= TOL
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 def test_stagewise_vs_reference_hooks(weights, backend):
     """Stage tensors of the coarse pass against the tensors hooked out of the reference's own modules."""
     g = load_golden("small_sym_up")

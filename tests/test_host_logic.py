@@ -117,7 +117,7 @@ def test_engine_dry_run(weights, monkeypatch, symmetric, upsample, split):
     eng.precision, eng.dtype, eng.dt = "fp32" if split else "fp32_simt", torch.float32, cabi.RB_F32
     eng.split, eng._lane, eng.generation = split, "main", 0
     eng.w = PackedWeights(weights[0], weights[1], eng.device, torch.float32, split=split)
-    eng._buf, eng._const, eng.debug, eng.profile, eng.gemm_profile, eng.use_flash_attn, eng.gp_algo = {}, {}, None, None, None, True, 2
+    eng._buf, eng._const, eng.debug, eng.profile, eng.gemm_profile, eng.use_flash_attn, eng.gp_algo = {}, {}, None, None, None, True, (3 if split else 2)
     eng.overlap_cnn, eng._side, eng.gp_tensor_core, eng.fused_c144, eng.fused_small_f32 = False, None, True, True, True
     for t in _tensors(eng.w):
         rec.track(t)
@@ -173,3 +173,58 @@ def test_layout_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "romatch import" not in text, f
+
+
+def test_cabi_call_validates_tensors():
+    """The ctypes shim refuses tensors whose device / dtype / layout / size contradict the call's description (a raw pointer of
+    the wrong kind would be silent garbage on the device)."""
+    a = torch.zeros(8, 8)
+    with pytest.raises(RuntimeError, match="expected the current CUDA device"):
+        cabi.call("romab200_gemm", "rb_gemm_args", A=a, B=a, C=a, M=8, N=8, K=8, lda=8, ldb=8, ldc=8, dtype_ab=cabi.RB_F32, dtype_c=cabi.RB_F32)
+    with pytest.raises(TypeError):
+        cabi.call("romab200_gemm", "rb_gemm_args", not_a_field=1)
+    # dtype / contiguity / size rules, exercised on the validator itself with the device check satisfied by a stand-in
+    class FakeCuda(torch.Tensor):
+        is_cuda = True
+
+        @property
+        def device(self):
+            return type("D", (), {"index": None})()
+    def fake(t):
+        return t.as_subclass(FakeCuda)
+    half, f32 = fake(torch.zeros(8, 8, dtype=torch.float16)), fake(torch.zeros(8, 8))
+    kw = dict(A=half, B=half, C=f32, M=8, N=8, K=8, lda=8, ldb=8, ldc=8, dtype_ab=cabi.RB_F32, dtype_c=cabi.RB_F32)
+    with pytest.raises(RuntimeError, match="dtype"):
+        cabi._validate("romab200_gemm", "rb_gemm_args", kw)
+    kw.update(A=f32, B=f32, M=16)
+    with pytest.raises(RuntimeError, match="needs"):
+        cabi._validate("romab200_gemm", "rb_gemm_args", kw)
+    kw.update(M=8, A=fake(torch.zeros(8, 16)[:, :8]))
+    with pytest.raises(RuntimeError, match="contiguous"):
+        cabi._validate("romab200_gemm", "rb_gemm_args", kw)
+    kw.update(A=f32)
+    cabi._validate("romab200_gemm", "rb_gemm_args", kw)
+
+
+def test_romatch_import_shim():
+    """`import romatch` through shim/ gives the reference's import surface backed by this package (romatch/__init__.py:2-8)."""
+    import importlib
+    import os
+    import sys
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shim")
+    sys.path.insert(0, shim)
+    try:
+        for m in [k for k in sys.modules if k == "romatch" or k.startswith("romatch.")]:
+            del sys.modules[m]
+        romatch = importlib.import_module("romatch")
+        import roma_b200
+        assert romatch.roma_outdoor is roma_b200.roma_outdoor and romatch.roma_indoor is roma_b200.roma_indoor
+        assert romatch.tiny_roma_v1_outdoor is roma_b200.tiny_roma_v1_outdoor
+        assert (romatch.DEBUG_MODE, romatch.GLOBAL_STEP, romatch.STEP_SIZE, romatch.LOCAL_RANK) == (False, 0, 1, -1) and isinstance(romatch.RANK, int)
+        zoo = importlib.import_module("romatch.models.model_zoo")
+        assert "outdoor" in zoo.weight_urls["romatch"] and zoo.roma_model is roma_b200.model_zoo.roma_model
+        assert importlib.import_module("romatch.models.matcher").RegressionMatcher is roma_b200.matcher.RegressionMatcher
+    finally:
+        sys.path.remove(shim)
+        for m in [k for k in sys.modules if k == "romatch" or k.startswith("romatch.")]:
+            del sys.modules[m]

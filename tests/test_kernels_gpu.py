@@ -200,8 +200,8 @@ def test_conv_first_and_maxpool():
 
 
 # ----------------------------------------------------------------------------------------------- GP solve
-@pytest.mark.parametrize("algo", [0, 1, 2])
-@pytest.mark.parametrize("n,nrhs,batch", [(64, 40, 2), (100, 512, 1), (1600, 512, 2), (224, 70, 3), (1408, 512, 2)])
+@pytest.mark.parametrize("algo", [0, 1, 2, 3])
+@pytest.mark.parametrize("n,nrhs,batch", [(64, 40, 2), (100, 512, 1), (1600, 512, 2), (224, 70, 3), (1408, 512, 2), (1600, 512, 5)])
 def test_gp_solve(n, nrhs, batch, algo):
     g = torch.Generator().manual_seed(n)
     feats = torch.randn(batch, n, 48, generator=g)
@@ -215,6 +215,8 @@ def test_gp_solve(n, nrhs, batch, algo):
     Wk[:, n:, :n] = Fm.t()
     Wk = Wk.to(DEV)
     ws_floats = max(batch * ((n + 31) // 32) * 1024 + 1, batch * ((n + 127) // 128) * 16384)
+    if algo == 3:         # block inverses + split-fp16 scratch pairs of the tensor-core variant (include/romab200.h)
+        ws_floats = batch * (((n + 127) // 128) * 16384 + max((n + nrhs) * 128 + 16384, nrhs * 128 + 16384 + 128 * ldw))
     ws = torch.empty(ws_floats, device=DEV)
     call("romab200_gp_solve", "rb_gp_solve_args", W=Wk, n=n, nrhs=nrhs, batch=batch, ldw=ldw, stride=(n + nrhs) * ldw,
          workspace=ws if algo else None, workspace_bytes=ws_floats * 4 if algo else 0, algo=algo)
@@ -222,7 +224,7 @@ def test_gp_solve(n, nrhs, batch, algo):
     alpha_t = Wk[:, n:, :n].cpu()
     err = (alpha_t.transpose(1, 2).double() - ref).abs().max().item()
     assert err < 5e-4 * ref.abs().max().item(), err
-    if algo != 1:            # in-place variants: the lower triangle now holds the Cholesky factor
+    if algo != 1:            # in-place variants (0, 2, 3): the lower triangle now holds the Cholesky factor
         L = torch.tril(Wk[:, :n, :n].cpu().double())
         close((L @ L.transpose(1, 2)).float(), Kyy, 1e-5)
 
@@ -399,3 +401,18 @@ def test_kde_density():
     call("romab200_kde_density", "rb_kde_args", x=x.to(DEV), density=out32, n=n, std=0.1, half=0)
     ref32 = (-torch.cdist(x.double(), x.double()) ** 2 / (2 * 0.1 ** 2)).exp().sum(-1)
     close(out32, ref32.float(), 2e-3)
+
+
+@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+def test_local_corr_warp_wheel_signature(mode):
+    """`romab200_local_corr_warp` = the fused-local-corr wheel's operator (local_correlation.py:22-35): arbitrary (non-lattice)
+    warps incl. samples outside the image, against F.grid_sample + dot product."""
+    B, C, H, W, K = 2, 48, 9, 11, 7
+    f0, f1 = rnd(B, H * W, C, seed=1), rnd(B, H, W, C, seed=2)
+    warp = (rnd(B, H * W, K, 2, seed=3) * 0.7).clamp(-1.3, 1.3).contiguous()
+    out = torch.zeros(B, H * W, K, device=DEV)
+    call("romab200_local_corr_warp", "rb_local_corr_warp_args", f0=f0, f1=f1, ldf0=C, ldf1=C, warp=warp, out=out, batch=B, h=H, w=W, c=C, k=K,
+         mode=0 if mode == "bilinear" else 1)
+    samp = F.grid_sample(f1.permute(0, 3, 1, 2), warp.reshape(B, H * W, K, 2), mode=mode, padding_mode="zeros", align_corners=False)   # [B,C,HW,K]
+    ref = torch.einsum("bpc,bcpk->bpk", f0, samp)
+    close(out, ref, 2e-5)

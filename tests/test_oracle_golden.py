@@ -40,6 +40,16 @@ def test_oracle_matches_reference_small(weights, name):
     assert warp.dtype == torch.float32 and cert.dtype == torch.float32
 
 
+def test_oracle_matches_reference_rectangular(weights):
+    """Non-square resolutions (112 x 168 -> 168 x 224): h and w differ in every grid, window and displacement scale."""
+    g = load_golden("rect_sym_up")
+    ch, cw, uh, uw = (int(v) for v in g["res"])
+    orc = RomaOracle(weights[0], weights[1], (ch, cw), (uh, uw), symmetric=True, upsample_preds=True)
+    A, B, Ah, Bh = synthetic.make_pair(1, (ch, cw), (uh, uw), int(g["meta"][5]))
+    warp, cert = orc.match(A, B, Ah, Bh)
+    _check(warp, cert, g)
+
+
 def test_oracle_stage_tensors(weights):
     g = load_golden("small_sym_up")
     orc = _oracle(weights, g)
