@@ -416,3 +416,96 @@ def test_local_corr_warp_wheel_signature(mode):
     samp = F.grid_sample(f1.permute(0, 3, 1, 2), warp.reshape(B, H * W, K, 2), mode=mode, padding_mode="zeros", align_corners=False)   # [B,C,HW,K]
     ref = torch.einsum("bpc,bcpk->bpk", f0, samp)
     close(out, ref, 2e-5)
+
+
+# ----------------------------------------------------------------------------------------------- 16-bit instantiations
+# The fast mode runs the __half / bf16 instantiations of the kernels below; each is pinned here against the oracle evaluated on the
+# SAME 16-bit-rounded inputs, so that only the kernel's own arithmetic (fp32 accumulation, one rounding at the store) is judged.
+DT16 = [torch.float16, torch.bfloat16]
+CODE16 = {torch.float16: cabi.RB_F16, torch.bfloat16: cabi.RB_BF16}
+EPS16 = {torch.float16: 2.0 ** -10, torch.bfloat16: 2.0 ** -7}        # relative spacing of the storage format (x2 margin below)
+
+
+@pytest.mark.parametrize("dt", DT16)
+@pytest.mark.parametrize("r,c,h,w", [(7, 512, 10, 12), (3, 512, 14, 14), (2, 256, 21, 17)])
+def test_local_corr_16bit(dt, r, c, h, w):
+    """local_corr_kernel<__half / bf16>: 16-bit features, fp32 accumulation; fp32 and 16-bit results."""
+    from oracle.roma_oracle import RomaOracle
+    B = 2
+    f0, f1 = rnd(B, c, h, w, seed=1).to(dt), rnd(B, c, h, w, seed=2).to(dt)
+    flow = (torch.rand(B, 2, h, w, generator=torch.Generator().manual_seed(3)) * 2.6 - 1.3)
+    ref = RomaOracle.local_correlation(f0.float().cpu(), f1.float().cpu(), r, flow)
+    K = (2 * r + 1) ** 2
+    f0c, f1c = f0.permute(0, 2, 3, 1).contiguous(), f1.permute(0, 2, 3, 1).contiguous()
+    fl = flow.permute(0, 2, 3, 1).contiguous().to(DEV)
+    wx, wy = _windows(r, h, w)
+    for out_dt, code in ((torch.float32, F32), (dt, CODE16[dt])):
+        out = torch.zeros(B, h, w, K, dtype=out_dt, device=DEV)
+        call("romab200_local_corr", "rb_local_corr_args", f0=f0c, f1=f1c, ldf0=c, ldf1=c, f0_img_stride=h * w * c, f1_img_stride=h * w * c,
+             flow=fl, ldflow=2, out=out, ldo=K, batch=B, h=h, w=w, c=c, radius=r, scale=1.0 / math.sqrt(c), dtype_f=CODE16[dt], dtype_out=code,
+             n_img=B, y_shift=0, win_x=wx, win_y=wy)
+        tol = 5e-5 if out_dt == torch.float32 else 2 * EPS16[dt] * ref.abs().max().item()
+        close(out.permute(0, 3, 1, 2), ref, tol)
+
+
+@pytest.mark.parametrize("dt", DT16)
+@pytest.mark.parametrize("s", [16, 8, 4, 2, 1])
+def test_refiner_prologue_and_tail_16bit(weights, dt, s):
+    """refiner_prologue_kernel<T, R> (x copy, grid_sample, displacement embedding, local correlation) and refiner_tail_kernel<T> on
+    16-bit maps against the oracle on the rounded features."""
+    from oracle.roma_oracle import RomaOracle
+    from roma_b200 import arch
+    from roma_b200.packing import pad8
+    spec = arch.REFINERS[s]
+    h, w = (6, 7) if s >= 4 else (12, 10)
+    E = D = 2
+    orc = RomaOracle(weights[0], weights[1])
+    feat = rnd(E, spec.feat, h, w, seed=s).to(dt)
+    flow = (torch.rand(D, 2, h, w, generator=torch.Generator().manual_seed(s + 1)) * 2.2 - 1.1)
+    cert = torch.randn(D, 1, h, w, generator=torch.Generator().manual_seed(s + 2))
+    fc = feat.float().cpu()
+    sf = 1.3
+    d_ref = orc.refiner_input(s, fc, torch.cat((fc[1:], fc[:1])), flow, sf)
+    R = _packed(weights).refiner[s]
+    cp, c = R["cp"], R["c"]
+    ldf = pad8(spec.feat)
+    featc = torch.zeros(E, h, w, ldf, dtype=dt, device=DEV)
+    featc[..., :spec.feat] = feat.permute(0, 2, 3, 1)
+    state = torch.cat((flow, cert), 1).permute(0, 2, 3, 1).contiguous().to(DEV)
+    state0 = state.clone()
+    d = torch.zeros(D * h * w, cp, dtype=dt, device=DEV)
+    gx = torch.linspace(-1 + 1 / w, 1 - 1 / w, w).to(DEV)
+    gy = torch.linspace(-1 + 1 / h, 1 - 1 / h, h).to(DEV)
+    r = spec.radius
+    wx, wy = _windows(r, h, w) if r else (None, None)
+    call("romab200_refiner_prologue", "rb_refiner_prologue_args", feat=featc, ldf=ldf, n_img=E, y_shift=1, state=state, d=d, ldd=cp,
+         D=D, h=h, w=w, cf=spec.feat, emb=spec.emb, radius=r, dtype=CODE16[dt], emb_weight=R["emb_w"], emb_bias=R["emb_b"],
+         disp_scale=float(torch.tensor(40 / 32 * sf, dtype=torch.float32)), grid_x=gx, grid_y=gy, win_x=wx, win_y=wy)
+    got = d.view(D, h, w, cp)[..., :c].permute(0, 3, 1, 2).float().cpu()
+    err = (got - d_ref).abs()
+    assert (err <= 2 * EPS16[dt] * d_ref.abs() + 1e-4).all(), err.max().item()        # one rounding of an fp32-accurate value
+    # tail: fp32 head on the 16-bit map
+    delta = torch.zeros(D * h * w, 3, device=DEV)
+    call("romab200_refiner_tail", "rb_refiner_tail_args", d=d, ldd=cp, weight=R["out_w"], ldw=cp, bias=R["out_b"], state=state,
+         rows=D * h * w, c=c, scale_x=0.5, scale_y=0.25, dtype=CODE16[dt], delta_out=delta)
+    ref_delta = d[:, :c].double() @ R["out_w"][:, :c].double().t() + R["out_b"].double()
+    close(delta, ref_delta, 2e-5 * max(1.0, ref_delta.abs().max().item()))
+    close(state, state0 + delta.view(D, h, w, 3) * torch.tensor([0.5, 0.25, 1.0], device=DEV), 1e-6)
+
+
+@pytest.mark.parametrize("dt", DT16)
+def test_cls_to_flow_refine_16bit(dt):
+    """cls_to_flow_kernel<__half / bf16>: softmax / argmax / 5-neighbour soft-argmax on 16-bit logits (fp32 inside)."""
+    from oracle.roma_oracle import RomaOracle
+    B, hh, ww = 2, 5, 6
+    cls = rnd(B, 4097, hh, ww, seed=1, scale=4.0).to(dt)
+    cls[0, :4096, 0, 0] = 0.0
+    cls[0, 4095, 0, 1] = 100.0
+    cls[0, 63, 0, 2] = 100.0
+    ref = RomaOracle.cls_to_flow_refine(cls[:, :4096].float().cpu())
+    logits = torch.zeros(B * hh * ww, 4104, dtype=dt, device=DEV)
+    logits[:, :4097] = cls.permute(0, 2, 3, 1).reshape(-1, 4097)
+    state = torch.zeros(B * hh * ww, 3, device=DEV)
+    call("romab200_cls_to_flow_refine", "rb_cls_args", logits=logits, state=state, rows=B * hh * ww, ldl=4104, res=64, dtype=CODE16[dt])
+    close(state[:, :2].reshape(B, hh, ww, 2), ref, 5e-6)
+    close(state[:, 2].reshape(B, hh, ww), cls[:, 4096].float(), 0)
