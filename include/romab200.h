@@ -63,8 +63,8 @@ int romab200_device_ok(void);
  * Epilogue RB_EPI_COSKERNEL: c = acc * s(m,n), s = 1/(na[m]*nb[n]+eps)            (cos_normalized == 0)
  *                                              s = na[m]*nb[n]/(na[m]*nb[n]+eps)  (operands pre-normalised)
  *                            v = exp((c - 1) * inv_t) + (m == n ? diag_add : 0)
- * Row map of the store: NONE; PAD_KEEP (m indexes a zero-padded [*,pad_h,pad_w] grid, border rows are
- * not written); PAD_TO_COMPACT (same, interior rows are written to the un-padded row index);
+ * Row map of the store: NONE; PAD_KEEP (m indexes a zero-padded [*,pad_h,pad_w] grid; border rows are not
+ * computed: they are left alone or rewritten with zeros, the value they hold in every map of the path); PAD_TO_COMPACT (same, interior rows are written to the un-padded row index);
  * SEGMENT (row m -> (m / seg_in) * seg_out + m % seg_in + seg_off).
  * Output pitch: the tcgen05 back-end stores tiles with TMA when ldc (and the batch strides) are multiples of 16 bytes; TMA clips at
  * 16-byte granules, so the pad columns N .. roundup(N, 16 bytes) of a written row receive zeros (columns beyond are untouched).

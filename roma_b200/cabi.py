@@ -148,7 +148,7 @@ def _gemm_min_elems(kw):
     if kw.get("rowmap", 0) == ROWMAP_PAD_TO_COMPACT:
         rows_out = M // (kw["pad_h"] * kw["pad_w"]) * (kw["pad_h"] - 2) * (kw["pad_w"] - 2)
     elif kw.get("rowmap", 0) == ROWMAP_SEGMENT:
-        rows_out = (M + kw["seg_in"] - 1) // kw["seg_in"] * kw["seg_out"] + kw.get("seg_off", 0)
+        rows_out = (M - 1) // kw["seg_in"] * kw["seg_out"] + (M - 1) % kw["seg_in"] + kw.get("seg_off", 0) + 1
     c = offc + (rows_out - 1) * kw["ldc"] + N
     return {"A": a, "A_lo": a, "B": b, "B_lo": b, "C": c, "C_lo": c}
 

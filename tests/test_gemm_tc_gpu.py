@@ -105,7 +105,9 @@ def test_tc_conv3x3_taps(dt, cin, cout, H, W):
     gemm(xp, wm, out, rows, cout, 9 * cin, cin, 9 * cin, cout, dt, dt, ntaps=9, tap_rows=taps, a_rows=rows, bias=b,
          act=cabi.ACT_RELU, rowmap=cabi.ROWMAP_PAD_KEEP, pad_h=H + 2, pad_w=W + 2)
     close(out[:, 1:-1, 1:-1], ref, 8e-2 if dt == torch.bfloat16 else 1e-2)
-    assert (out[:, 0] == -5.0).all() and (out[:, :, -1] == -5.0).all()
+    # border rows of a padded map: left alone (direct stores) or rewritten with the zeros they hold on the path (TMA-store epilogue)
+    border = torch.cat((out[:, 0].flatten(), out[:, -1].flatten(), out[:, :, 0].flatten(), out[:, :, -1].flatten()))
+    assert ((border == -5.0) | (border == 0.0)).all()
 
 
 def test_tc_coskernel_split_f16x3_is_fp32_class():
