@@ -286,6 +286,20 @@ int romab200_match_epilogue(const rb_match_epilogue_args* args, void* stream);
 typedef struct { const float* x; float* density; int32_t n; float std; int32_t half; } rb_kde_args;
 int romab200_kde_density(const rb_kde_args* args, void* stream);
 
+/* sample(): weighted sampling WITHOUT replacement on the device (the two torch.multinomial draws of matcher.py:613-617, 626-628).
+ * For every batch item b: draws k distinct indices i in [0, n) with probabilities proportional to w_i = T(values[b*stride + i]),
+ *   T = identity (RB_SAMPLE_IDENTITY), certainty thresholding `v > param ? 1 : v` (RB_SAMPLE_THRESHOLD, matcher.py:604-607), or density
+ *   balancing `v < 10 ? 1e-7 : 1/(v+1)` of a KDE density v (RB_SAMPLE_BALANCE, matcher.py:622-625),
+ * by an exponential race (key = -log(u)/w, k smallest keys; Philox4x32-10 keyed by `seed`, counter = element index).  out_idx [batch, k]
+ * int32 in no particular order; out_weights (optional) [batch, k] receives the transformed weights of the drawn items; keys = workspace of
+ * batch * n floats.  Items of zero weight are only drawn when fewer than k positive weights exist. */
+enum rb_sample_transform { RB_SAMPLE_IDENTITY = 0, RB_SAMPLE_THRESHOLD = 1, RB_SAMPLE_BALANCE = 2 };
+typedef struct {
+    const float* values; int64_t n; int32_t k; int32_t batch; int64_t stride; uint64_t seed; int32_t transform; float param;
+    int32_t* out_idx; float* out_weights; float* keys;
+} rb_sample_args;
+int romab200_weighted_sample(const rb_sample_args* args, void* stream);
+
 /* transpose a batched strided 2-D matrix: dst[b][c][r] = src[b][r][c]  (V^T for the PV product) */
 typedef struct {
     const void* src; void* dst; int32_t rows, cols; int64_t lds, ldd; int32_t batch0, batch1;

@@ -23,11 +23,12 @@ ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 ROWMAP_NONE, ROWMAP_PAD_KEEP, ROWMAP_PAD_TO_COMPACT, ROWMAP_SEGMENT = 0, 1, 2, 3
 EPI_LINEAR, EPI_COSKERNEL = 0, 1
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
+SAMPLE_IDENTITY, SAMPLE_THRESHOLD, SAMPLE_BALANCE = 0, 1, 2
 
 DTYPE_CODE = {torch.float32: RB_F32, torch.float16: RB_F16, torch.bfloat16: RB_BF16}
 
 _CTYPES = {
-    "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float,
+    "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "float": ctypes.c_float,
 }
 
 
@@ -131,7 +132,7 @@ _FIELD_DTYPES = {
     "rb_resize_args": {"in": _F32, "out": _F32},
     "rb_match_epilogue_args": {"state": _F32, "coarse_state": _F32, "warp": _F32, "cert": _F32, "grid_x": _F32, "grid_y": _F32},
     "rb_kde_args": {"x": _F32, "density": _F32},
-    "rb_sample_args": {"weights": _F32, "keys": _F32},
+    "rb_sample_args": {"values": _F32, "out_idx": torch.int32, "out_weights": _F32, "keys": _F32},
 }
 
 

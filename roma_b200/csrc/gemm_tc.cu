@@ -140,8 +140,8 @@ struct TcParams {
     int tiles_m, tiles_n, total_tiles;
     int64_t sc0, sc1, sr0, sr1, sna0, snb0;
     unsigned long long* clk;      // optional role-time counters (ROMAB200_TC_CLK=1): see tc_clk_dump
-    int epi_mode;                 // store strategy of the epilogue: 0 = direct row-per-lane stores, 1 = shared-memory transpose,
-                                  // 2 = TMA stores from a per-warp staging buffer (map_c / map_c_lo), 3 = the same as an fp32 reduce-add (C += tile)
+    int epi_mode;                 // store strategy of the epilogue: 0 = direct row-per-lane stores, 2 = TMA stores from a per-warp staging
+                                  // buffer (map_c / map_c_lo), 3 = the same as an fp32 reduce-add (C += tile)
     Epilogue epi;
 };
 
@@ -151,7 +151,7 @@ struct TcParams {
 __device__ __forceinline__ void clk_add(unsigned long long* clk, int i, long long v) { if (clk) atomicAdd(&clk[i], (unsigned long long)v); }
 
 constexpr int TC_BM = 128, TC_BK = 64;
-constexpr int TC_STAGE_WORDS = 32 * 20;            // epilogue transpose buffer per warp: 32 rows x 16 words, row pitch 20 words
+constexpr int TC_STAGE_WORDS = 512;                // TMA-store staging buffer per epilogue warp: 32 rows x 64 bytes
 
 template <int BN, bool SPLIT> struct TcCfg {
     // BN = 256: one CTA per SM with 8 epilogue warps; narrower tiles: two CTAs per SM (two MMA-issuing threads keep the
@@ -185,12 +185,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // further.  (m0, n0) = first row / column of the tile, z0 / z1 = batch indices.
 //
 // tcgen05.ld hands every lane ONE ROW of the accumulator, so a direct store writes 16-byte pieces of 32 different rows per
-// instruction: 32 cache lines touched per instruction, and measured (clock64 counters, scripts/gemm_clk.py) 16-19k cycles per
-// 128 x 256 tile against 8k (f16) / 25k (split) cycles of MMA work.  Each warp therefore transposes its 32 x 32 chunk through a
-// private 32 x 16-word staging buffer in shared memory (two halves, row pitch 20 words: conflict-free 16-byte accesses both
-// ways) and stores with 4 lanes per row: every instruction writes whole 32-byte sectors of 8 rows, and the residual operand is
-// read the same way.
-
+// instruction.  Measured with the role-time counters (ROMAB200_TC_CLK=1, scripts/gemm_clk.py) on the ViT shapes, cycles per
+// 128 x 256 tile: store phase 6.1k (f16 out) / 11.6k (split pair out) against 8k / 25k cycles of MMA work; a shared-memory
+// transpose to 4-lanes-per-row stores was slower still (12-15k: more instructions, the same line-granular L1 path).  So the
+// tile leaves through the TMA unit instead: every warp writes its 32 x 32 chunk into a private 2 KB staging buffer as
+// [32 rows][64 B] and one lane issues cp.async.bulk.tensor stores (UTMASTG; 3.3k / 5.6k cycles, asynchronous to the warp); an
+// in-place fp32 residual (R == C) becomes a TMA reduce-add (UTMAREDG), so the residual stream is never read by the kernel.
+// Row maps other than NONE / PAD_KEEP, mismatched residual operands and unaligned pitches take the direct path.
 template <int BN, bool SPLIT, int EPI_WARPS>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tmem_acc, uint64_t* full_bar, uint32_t full_parity, int m0, int n0,
                                                  int z0, int z1, int q, int half, int lane, int et, float* s_vec0, float* s_vec1, float* stage,
@@ -221,12 +222,9 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
     const int nlim = min(p.N, n0 + BN);                  // columns of this tile (BN need not be a multiple of 32)
     const int m = m0 + q * 32 + lane;
     const int64_t orow = m < p.M ? e.map_row(m) : -1;
-    const int orow_lo = (int)(orow & 0xffffffff), orow_hi = (int)(orow >> 32);
     const int es_c = dtype_size(e.dtype_c);
     const bool vec_ok = (e.ldc * es_c) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.C) % 16 == 0) &&
                         (e.dtype_c != RB_F16S || reinterpret_cast<uintptr_t>(e.C_lo) % 16 == 0);
-    const bool rvec_ok = e.R && e.dtype_r == RB_F32 && (e.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(e.R) & 15) == 0;
-    const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;          // store phase: 4 lanes per row, 4 columns per lane
 #pragma unroll 1
     for (int cb = half * 32; cb < BN; cb += 8 * EPI_WARPS) {
         if (n0 + cb >= nlim) break;                     // warp-uniform
@@ -282,7 +280,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
                 }
             }
         }
-        // ---- transpose through the warp's staging buffer and store (residual added here, read coalesced) ----
+        // ---- store ----
         long long tc2 = clock64();
         t_math += tc2 - tc1;
         if (p.epi_mode >= 2) {
@@ -437,57 +435,6 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
                 if (nb + j < nlim) store_split_any(e.C, e.C_lo, orow * e.ldc + nb + j, e.dtype_c, v[j]);
         }
             }
-        } else {
-    #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            __syncwarp();                               // the previous half has been read by every lane
-    #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<float4*>(&stage[lane * 20 + 4 * j]) = make_float4(v[16 * h + 4 * j], v[16 * h + 4 * j + 1], v[16 * h + 4 * j + 2], v[16 * h + 4 * j + 3]);
-            __syncwarp();
-    #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int r = it * 8 + sub_r;
-                const int64_t orow_r = ((int64_t)__shfl_sync(0xffffffffu, orow_hi, r) << 32) | (uint32_t)__shfl_sync(0xffffffffu, orow_lo, r);
-                const int n = nb + 16 * h + sub_c;
-                if (orow_r < 0 || n >= nlim) continue;          // no warp-synchronous operation below
-                float4 x = *reinterpret_cast<const float4*>(&stage[r * 20 + sub_c]);
-                const int nvalid = nlim - n;                    // >= 1
-                if (e.R) {
-                    if (rvec_ok && nvalid >= 4) {
-                        const float4 rr = *reinterpret_cast<const float4*>((const float*)e.R + orow_r * e.ldr + n);
-                        x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-                    } else {
-                        float* xs = reinterpret_cast<float*>(&x);
-    #pragma unroll
-                        for (int t = 0; t < 4; ++t) if (t < nvalid) xs[t] += load_any(e.R, orow_r * e.ldr + n + t, e.dtype_r);
-                    }
-                }
-                const int64_t off = orow_r * e.ldc + n;
-                if (vec_ok && nvalid >= 4) {
-                    if (e.dtype_c == RB_F32) {
-                        *reinterpret_cast<float4*>((float*)e.C + off) = x;
-                    } else if (e.dtype_c == RB_F16S) {
-                        const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
-                        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-                        const __half2 l0 = __floats2half2_rn((x.x - f0.x) * 2048.0f, (x.y - f0.y) * 2048.0f);
-                        const __half2 l1 = __floats2half2_rn((x.z - f1.x) * 2048.0f, (x.w - f1.y) * 2048.0f);
-                        *reinterpret_cast<uint2*>((uint16_t*)e.C + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-                        *reinterpret_cast<uint2*>((uint16_t*)e.C_lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
-                    } else if (e.dtype_c == RB_F16) {
-                        const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
-                        *reinterpret_cast<uint2*>((uint16_t*)e.C + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-                    } else {
-                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
-                        *reinterpret_cast<uint2*>((uint16_t*)e.C + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-                    }
-                } else {
-                    const float* xs = reinterpret_cast<const float*>(&x);
-    #pragma unroll
-                    for (int t = 0; t < 4; ++t) if (t < nvalid) store_split_any(e.C, e.C_lo, off + t, e.dtype_c, xs[t]);
-                }
-            }
-        }
         }
         __syncwarp();
         if (timing) { t_store += clock64() - tc2; }
@@ -1040,7 +987,7 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
     p.sc0 = a->sc0; p.sc1 = a->sc1; p.sr0 = a->sr0; p.sr1 = a->sr1; p.sna0 = a->sna0; p.snb0 = a->snb0;
     p.epi = make_epilogue(a);
     p.clk = tc_clk_buffer();
-    { static const int em = [] { const char* e = getenv("ROMAB200_GEMM_EPI"); return e ? atoi(e) : 2; }(); p.epi_mode = em; }
+    { static const int em = [] { const char* e = getenv("ROMAB200_GEMM_EPI"); return e && atoi(e) == 0 ? 0 : 2; }(); p.epi_mode = em; }
     if (p.ntaps > 1) {
         RB_REQUIRE(a->K % p.ntaps == 0 && p.k_per_tap % TC_BK == 0, "gemm_tc: K/ntaps=%d must be a multiple of %d", p.k_per_tap, TC_BK);
         RB_REQUIRE(!a->trans_b && batch0 * p.batch1 == 1, "gemm_tc: taps need un-batched [N,K] weights");

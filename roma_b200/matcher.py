@@ -36,6 +36,7 @@ class RegressionMatcher:
         self.symmetric = symmetric
         self.sample_thresh = sample_thresh
         self.training = False
+        self.device_sampler = True      # sample(): weighted sampling without replacement in one kernel per draw (False: torch.multinomial)
         self.use_cuda_graph = True      # replay the whole device side of match() as one CUDA graph per input shape
         self._graphs = {}
         self.graph_launches = 0         # kernels launched through graph replays (cabi.kernel_launches counts eager ones)
@@ -199,9 +200,14 @@ class RegressionMatcher:
 
     # ---- sampling (matcher.py:598-629) ----------------------------------------------------------------
     def sample(self, matches, certainty, num=10000):
-        """Certainty-thresholded, density-balanced match sampling.  Both `torch.multinomial` draws are kept
-        (same RNG stream semantics as the reference); the 4*num x 4*num Gaussian KDE runs in
-        `romab200_kde_density` without materialising the matrix."""
+        """Certainty-thresholded, density-balanced match sampling (matcher.py:598-629).  Both weighted draws without
+        replacement run on the device (`romab200_weighted_sample`: exponential race + radix select, the certainty
+        thresholding and the density balancing fused into the key computation) and the 4*num x 4*num Gaussian KDE in
+        `romab200_kde_density` without materialising the matrix; the seeds of the two draws come from torch's CPU generator,
+        so `torch.manual_seed` makes the result reproducible.  With `device_sampler = False` the two `torch.multinomial`
+        calls of the reference are used instead (same distribution, torch's RNG stream)."""
+        if self.device_sampler and matches.is_cuda:
+            return self._sample_device(matches, certainty, num)
         if "threshold" in self.sample_mode:
             upper_thresh = self.sample_thresh
             certainty = certainty.clone()
@@ -220,6 +226,32 @@ class RegressionMatcher:
         p[density < 10] = 1e-7      # at least ~10 perfect neighbours, as in the reference
         balanced_samples = torch.multinomial(p, num_samples=min(num, len(good_certainty)), replacement=False)
         return good_matches[balanced_samples], good_certainty[balanced_samples]
+
+    def _sample_device(self, matches, certainty, num):
+        balanced = "balanced" in self.sample_mode
+        with torch.cuda.device(matches.device):
+            m = matches.reshape(-1, 4).contiguous().float()
+            c = certainty.reshape(-1).contiguous().float()
+            n = c.numel()
+            k1 = min((4 if balanced else 1) * num, n)
+            seeds = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64).tolist()          # CPU generator: follows torch.manual_seed
+            idx1 = torch.empty(k1, dtype=torch.int32, device=m.device)
+            w1 = torch.empty(k1, dtype=torch.float32, device=m.device)
+            keys = torch.empty(n, dtype=torch.float32, device=m.device)
+            thresholded = "threshold" in self.sample_mode
+            cabi.call("romab200_weighted_sample", "rb_sample_args", values=c, n=n, k=k1, batch=1, stride=n, seed=seeds[0],
+                      transform=cabi.SAMPLE_THRESHOLD if thresholded else cabi.SAMPLE_IDENTITY, param=float(self.sample_thresh),
+                      out_idx=idx1, out_weights=w1, keys=keys)
+            good_matches = m[idx1.long()]
+            if not balanced:
+                return good_matches, w1
+            density = self.engine.kde(good_matches, std=0.1, half=True).to(torch.float16).float().contiguous()     # kde.py: x.half()
+            k2 = min(num, k1)
+            idx2 = torch.empty(k2, dtype=torch.int32, device=m.device)
+            cabi.call("romab200_weighted_sample", "rb_sample_args", values=density, n=k1, k=k2, batch=1, stride=k1, seed=seeds[1],
+                      transform=cabi.SAMPLE_BALANCE, param=0.0, out_idx=idx2, out_weights=None, keys=keys)
+            sel = idx2.long()
+            return good_matches[sel], w1[sel]
 
     # ---- small geometry helpers (matcher.py:672-773) ---------------------------------------------------
     def _to_pixel_coordinates(self, coords, H, W):

@@ -131,19 +131,66 @@ def test_api_errors_and_forward(weights):
 
 
 def test_sample_statistics(weights):
-    """sample(): same draws as the reference are impossible (different KDE rounding feeds the second
-    multinomial), so check the contract: shapes, membership, certainty thresholding and density balancing."""
+    """sample(): shapes, membership in the warp and certainty thresholding, for the device sampler and the torch.multinomial route
+    (the distribution itself is compared with the oracle in test_sample_distribution_vs_oracle)."""
     g = load_golden("small_sym_up")
     model = build(weights, g)
     warp = torch.from_numpy(g["warp"]).cuda()
     cert = torch.from_numpy(g["certainty"]).cuda()
-    torch.manual_seed(0)
-    m, c = model.sample(warp[0], cert[0], num=500)
-    assert m.shape == (500, 4) and c.shape == (500,)
-    # every sampled match is (bit-exactly) a row of the warp
     rows = {tuple(r) for r in warp[0].reshape(-1, 4).cpu().numpy().view("uint32").tolist()}
-    assert all(tuple(r) in rows for r in m.cpu().numpy().view("uint32").tolist())
-    assert ((c == 1) | (c <= model.sample_thresh)).all()
+    for device_sampler in (True, False):
+        model.device_sampler = device_sampler
+        torch.manual_seed(0)
+        m, c = model.sample(warp[0], cert[0], num=500)
+        assert m.shape == (500, 4) and c.shape == (500,)
+        # every sampled match is (bit-exactly) a row of the warp
+        assert all(tuple(r) in rows for r in m.cpu().numpy().view("uint32").tolist())
+        assert ((c == 1) | (c <= model.sample_thresh)).all()
+        torch.manual_seed(0)
+        m2, _ = model.sample(warp[0], cert[0], num=500)
+        assert torch.equal(m2, m) or not device_sampler          # the device sampler is reproducible under torch.manual_seed
+
+
+def test_sample_distribution_vs_oracle(weights):
+    """Acceptance test of the device-side sampler: RNG-stream parity with torch is impossible, so the sampled-match
+    distribution of `model.sample` is compared with the oracle's `sample` (the reference's algorithm: two torch.multinomial draws
+    around the fp16 KDE) over 60 seeds each: two-sample Kolmogorov-Smirnov on every coordinate and on the certainty, a chi-square
+    test on a 6 x 6 histogram of the query position, and the agreement of the `density < 10` mask on a fixed first draw."""
+    from scipy import stats
+    from oracle.roma_oracle import RomaOracle
+    g = load_golden("small_sym_up")
+    model = build(weights, g)
+    orc = RomaOracle(weights[0], weights[1], 112, 168)
+    warp, cert = torch.from_numpy(g["warp"])[0], torch.from_numpy(g["certainty"])[0]
+    wd, cd = warp.cuda(), cert.cuda()
+    ours, ref = [], []
+    for seed in range(60):
+        torch.manual_seed(1000 + seed)
+        m, c = model.sample(wd, cd, num=400)
+        assert m.shape == (400, 4) and c.shape == (400,)
+        ours.append(torch.cat((m, c[:, None]), 1).cpu())
+        torch.manual_seed(5000 + seed)
+        m, c = orc.sample(warp, cert, num=400)
+        ref.append(torch.cat((m, c[:, None].float()), 1))
+    ours, ref = torch.cat(ours).numpy(), torch.cat(ref).numpy()
+    rows = {tuple(r) for r in warp.reshape(-1, 4).numpy().view("uint32").tolist()}
+    assert all(tuple(r) in rows for r in np.ascontiguousarray(ours[:, :4]).view("uint32").tolist())      # every sample is a row of the warp
+    for j in range(5):
+        p = stats.ks_2samp(ours[:, j], ref[:, j]).pvalue
+        assert p > 1e-3, (j, p)
+    bins = np.linspace(-1, 1, 7)
+    h_o, _, _ = np.histogram2d(ours[:, 0], ours[:, 1], bins=(bins, bins))
+    h_r, _, _ = np.histogram2d(ref[:, 0], ref[:, 1], bins=(bins, bins))
+    keep = (h_o + h_r) > 20
+    chi2 = stats.chi2_contingency(np.stack((h_o[keep], h_r[keep])))
+    assert chi2[1] > 1e-3, chi2[1]
+    # density mask: the same first draw through both KDE implementations
+    torch.manual_seed(7)
+    good = warp.reshape(-1, 4)[torch.multinomial((cert.reshape(-1) > 0.05).float() + cert.reshape(-1) * (cert.reshape(-1) <= 0.05), 1600)]
+    d_ref = RomaOracle.kde(good)
+    d_ours = model.engine.kde(good.cuda(), std=0.1, half=True).to(torch.float16).cpu()
+    mismatch = ((d_ref < 10) != (d_ours < 10)).float().mean().item()
+    assert mismatch <= 2e-3, mismatch
 
 
 @pytest.mark.slow

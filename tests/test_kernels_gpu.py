@@ -509,3 +509,49 @@ def test_cls_to_flow_refine_16bit(dt):
     call("romab200_cls_to_flow_refine", "rb_cls_args", logits=logits, state=state, rows=B * hh * ww, ldl=4104, res=64, dtype=CODE16[dt])
     close(state[:, :2].reshape(B, hh, ww, 2), ref, 5e-6)
     close(state[:, 2].reshape(B, hh, ww), cls[:, 4096].float(), 0)
+
+
+# ----------------------------------------------------------------------------------------------- device-side sampling
+def test_weighted_sample_kernel_is_a_draw_without_replacement():
+    """romab200_weighted_sample: k distinct indices, never an item of zero weight while positive ones remain, inclusion frequencies
+    proportional to the weights (for k << n), the three weight transforms, batching, determinism under the seed."""
+    n, k, B = 20000, 500, 3
+    g = torch.Generator().manual_seed(0)
+    vals = torch.rand(B, n, generator=g)
+    vals[:, ::7] = 0.0                                     # zero weights are never drawn
+    vals = vals.to(DEV).contiguous()
+
+    def draw(seed, transform=cabi.SAMPLE_IDENTITY, param=0.0, values=vals, kk=k):
+        idx = torch.full((values.shape[0], kk), -1, dtype=torch.int32, device=DEV)
+        w = torch.zeros(values.shape[0], kk, device=DEV)
+        keys = torch.empty(values.shape[0] * values.shape[1], device=DEV)
+        call("romab200_weighted_sample", "rb_sample_args", values=values, n=values.shape[1], k=kk, batch=values.shape[0], stride=values.shape[1],
+             seed=seed, transform=transform, param=param, out_idx=idx, out_weights=w, keys=keys)
+        return idx.long(), w
+    idx, w = draw(1)
+    for b in range(B):
+        assert idx[b].min() >= 0 and idx[b].unique().numel() == k
+        assert (vals[b][idx[b]] > 0).all() and torch.equal(w[b], vals[b][idx[b]])
+    assert torch.equal(draw(1)[0].sort(-1).values, idx.sort(-1).values) and not torch.equal(draw(2)[0].sort(-1).values, idx.sort(-1).values)
+    assert not torch.equal(idx[0].sort().values, idx[1].sort().values)          # batch items use different streams
+    # inclusion frequency ~ weight: items of weight in [0.9, 1] are drawn ~9.5x as often as items in [0.05, 0.15]
+    hi = ((vals[0] >= 0.9)).float()
+    lo = ((vals[0] > 0.05) & (vals[0] <= 0.15)).float()
+    cnt = torch.zeros(n, device=DEV)
+    for s in range(200):
+        cnt[draw(100 + s)[0][0]] += 1
+    ratio = ((cnt * hi).sum() / hi.sum()) / ((cnt * lo).sum() / lo.sum())
+    assert 8.0 < ratio.item() < 11.0, ratio.item()
+    # transforms: thresholding makes everything above the threshold equally likely; balancing implements 1/(d+1) with the d < 10 floor
+    idx_t, w_t = draw(3, cabi.SAMPLE_THRESHOLD, 0.05)
+    assert ((w_t[0] == 1.0) | (w_t[0] <= 0.05)).all() and (w_t[0] == 1.0).float().mean() > 0.95
+    dens = torch.cat((torch.full((1, 5000), 3.0), torch.full((1, 5000), 50.0), torch.full((1, 5000), 500.0)), 1).to(DEV)
+    idx_b, _ = draw(4, cabi.SAMPLE_BALANCE, 0.0, values=dens, kk=1000)
+    frac = [(idx_b[0] // 5000 == j).float().mean().item() for j in range(3)]
+    assert frac[0] < 0.01 and 0.85 < frac[1] < 0.95 and 0.05 < frac[2] < 0.15, frac          # 1e-7 : 1/51 : 1/501
+    # k == n returns every index once; more draws than positive weights falls back to zero-weight items
+    small = torch.tensor([[0.0, 1.0, 2.0, 0.0, 3.0]], device=DEV)
+    all_idx, _ = draw(5, values=small, kk=5)
+    assert sorted(all_idx[0].tolist()) == [0, 1, 2, 3, 4]
+    three, _ = draw(6, values=small, kk=3)
+    assert sorted(three[0].tolist()) == [1, 2, 4]
