@@ -292,11 +292,12 @@ int romab200_kde_density(const rb_kde_args* args, void* stream);
  *   balancing `v < 10 ? 1e-7 : 1/(v+1)` of a KDE density v (RB_SAMPLE_BALANCE, matcher.py:622-625),
  * by an exponential race (key = -log(u)/w, k smallest keys; Philox4x32-10 keyed by `seed`, counter = element index).  out_idx [batch, k]
  * int32 in no particular order; out_weights (optional) [batch, k] receives the transformed weights of the drawn items; keys = workspace of
- * batch * n floats.  Items of zero weight are only drawn when fewer than k positive weights exist. */
+ * batch * n floats, scratch = workspace of batch * 2056 int32.  Items of zero weight are only drawn when fewer than k positive weights exist. */
 enum rb_sample_transform { RB_SAMPLE_IDENTITY = 0, RB_SAMPLE_THRESHOLD = 1, RB_SAMPLE_BALANCE = 2 };
 typedef struct {
     const float* values; int64_t n; int32_t k; int32_t batch; int64_t stride; uint64_t seed; int32_t transform; float param;
     int32_t* out_idx; float* out_weights; float* keys;
+    void* scratch;   /* batch * 2056 * 4 bytes: histograms and selection state (cleared inside the call) */
 } rb_sample_args;
 int romab200_weighted_sample(const rb_sample_args* args, void* stream);
 

@@ -236,21 +236,23 @@ class RegressionMatcher:
             k1 = min((4 if balanced else 1) * num, n)
             seeds = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64).tolist()          # CPU generator: follows torch.manual_seed
             idx1 = torch.empty(k1, dtype=torch.int32, device=m.device)
-            w1 = torch.empty(k1, dtype=torch.float32, device=m.device)
             keys = torch.empty(n, dtype=torch.float32, device=m.device)
+            scratch = torch.empty(2056, dtype=torch.int32, device=m.device)
             thresholded = "threshold" in self.sample_mode
             cabi.call("romab200_weighted_sample", "rb_sample_args", values=c, n=n, k=k1, batch=1, stride=n, seed=seeds[0],
                       transform=cabi.SAMPLE_THRESHOLD if thresholded else cabi.SAMPLE_IDENTITY, param=float(self.sample_thresh),
-                      out_idx=idx1, out_weights=w1, keys=keys)
-            good_matches = m[idx1.long()]
+                      out_idx=idx1, out_weights=None, keys=keys, scratch=scratch)
+            sel1 = idx1.long().sort().values                 # the compaction order is not deterministic; the drawn SET is
+            good_matches = m[sel1]
+            w1 = torch.where(c[sel1] > self.sample_thresh, torch.ones((), device=m.device), c[sel1]) if thresholded else c[sel1]
             if not balanced:
                 return good_matches, w1
             density = self.engine.kde(good_matches, std=0.1, half=True).to(torch.float16).float().contiguous()     # kde.py: x.half()
             k2 = min(num, k1)
             idx2 = torch.empty(k2, dtype=torch.int32, device=m.device)
             cabi.call("romab200_weighted_sample", "rb_sample_args", values=density, n=k1, k=k2, batch=1, stride=k1, seed=seeds[1],
-                      transform=cabi.SAMPLE_BALANCE, param=0.0, out_idx=idx2, out_weights=None, keys=keys)
-            sel = idx2.long()
+                      transform=cabi.SAMPLE_BALANCE, param=0.0, out_idx=idx2, out_weights=None, keys=keys, scratch=scratch)
+            sel = idx2.long().sort().values
             return good_matches[sel], w1[sel]
 
     # ---- small geometry helpers (matcher.py:672-773) ---------------------------------------------------

@@ -525,8 +525,9 @@ def test_weighted_sample_kernel_is_a_draw_without_replacement():
         idx = torch.full((values.shape[0], kk), -1, dtype=torch.int32, device=DEV)
         w = torch.zeros(values.shape[0], kk, device=DEV)
         keys = torch.empty(values.shape[0] * values.shape[1], device=DEV)
+        scratch = torch.empty(values.shape[0] * 2056, dtype=torch.int32, device=DEV)
         call("romab200_weighted_sample", "rb_sample_args", values=values, n=values.shape[1], k=kk, batch=values.shape[0], stride=values.shape[1],
-             seed=seed, transform=transform, param=param, out_idx=idx, out_weights=w, keys=keys)
+             seed=seed, transform=transform, param=param, out_idx=idx, out_weights=w, keys=keys, scratch=scratch)
         return idx.long(), w
     idx, w = draw(1)
     for b in range(B):
