@@ -111,6 +111,58 @@ def cpu_reference_time(steps, warmup, budget_s=240.0, with_sample=True):
     return times, torch.get_num_threads()
 
 
+def local_corr_flow_sweep(dev, precision):
+    """The local-correlation prologue kernels alone, on smooth flow (identity + 0.5 pixel of noise: neighbouring pixels share their
+    windows) and on random flow (uniform over the image: no sharing, what the seeded synthetic weights produce): ms per launch and the
+    compulsory HBM bytes of SURVEY 8d (read f0 + f1 + flow, write the window) per second, for the five launches of one direction pair."""
+    import torch
+    from roma_b200 import arch, cabi
+    from roma_b200.cabi import call
+    dt = torch.float32 if precision.startswith("fp32") else (torch.float16 if precision == "fp16" else torch.bfloat16)
+    code = cabi.DTYPE_CODE[dt]
+    es = 4 if dt == torch.float32 else 2
+    g = torch.Generator(device="cpu").manual_seed(0)
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for kind in ("smooth", "random"):
+        tot_ms, tot_bytes, per = 0.0, 0.0, {}
+        for res, scales in ((COARSE, (16, 8, 4)), (UPSAMPLE, (8, 4))):
+            for sc in scales:
+                spec = arch.REFINERS[sc]
+                h = w = res // sc if sc != 16 else res // 14
+                D = E = 2
+                ldf = (spec.feat + 7) // 8 * 8
+                cp = (spec.channels + 7) // 8 * 8
+                feat = torch.randn(E, h, w, ldf, generator=g).to(dev, dt)
+                ys, xs = torch.linspace(-1 + 1 / h, 1 - 1 / h, h), torch.linspace(-1 + 1 / w, 1 - 1 / w, w)
+                gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+                ident = torch.stack((gx, gy), -1)[None].expand(D, h, w, 2)
+                flow = ident + torch.randn(D, h, w, 2, generator=g) * (1.0 / w) if kind == "smooth" else torch.rand(D, h, w, 2, generator=g) * 2 - 1
+                state = torch.cat((flow, torch.zeros(D, h, w, 1)), -1).contiguous().to(dev)
+                d = torch.zeros(D * h * w, cp, dtype=dt, device=dev)
+                r = spec.radius
+                wx = torch.linspace(-2 * r / w, 2 * r / w, 2 * r + 1).to(dev)
+                wy = torch.linspace(-2 * r / h, 2 * r / h, 2 * r + 1).to(dev)
+                R = dict(emb_w=torch.randn(spec.emb, 2).to(dev), emb_b=torch.randn(spec.emb).to(dev))
+                kw = dict(feat=feat, ldf=ldf, n_img=E, y_shift=1, state=state, d=d, ldd=cp, D=D, h=h, w=w, cf=spec.feat, emb=spec.emb, radius=r, dtype=code,
+                          emb_weight=R["emb_w"], emb_bias=R["emb_b"], disp_scale=1.25, grid_x=xs.to(dev), grid_y=ys.to(dev), win_x=wx, win_y=wy)
+                for _ in range(2):
+                    call("romab200_refiner_prologue", "rb_refiner_prologue_args", **kw)
+                ts = []
+                for _ in range(5):
+                    flush.zero_()
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record(); call("romab200_refiner_prologue", "rb_refiner_prologue_args", **kw); e.record()
+                    torch.cuda.synchronize()
+                    ts.append(s.elapsed_time(e))
+                ms = sorted(ts)[2]
+                nbytes = D * h * w * ((2 * spec.feat + spec.k) * es + 8)        # f0 + f1 read once, window written once, flow read
+                per[f"stride{sc}@{res}"] = {"ms": round(ms, 4), "gbs": round(nbytes / ms / 1e6, 1)}
+                tot_ms += ms; tot_bytes += nbytes
+        out[kind] = {"ms_per_pair": round(tot_ms, 4), "hbm_gbs": round(tot_bytes / tot_ms / 1e6, 1), "launches": per}
+    return out
+
+
 def torch_cuda_baseline(dev, steps=5, warmup=2, with_sample=True):
     """The "existing Blackwell kernels" bar: the same graph through stock PyTorch on this GPU — the oracle's
     torch.nn.functional restatement of the reference with weights and inputs on `cuda`, i.e. cuDNN convolutions, cuBLAS GEMMs, SDPA
@@ -456,6 +508,10 @@ def run_ours(args):
                           "launches_per_step": cos_n / args.steps, "ms_per_step": cos_ms / args.steps,
                           "note": "four 1600x1600x512 problems per pair (2.6 GFLOP each, 1.5 us at peak): size-limited, see DESIGN.md"})
         lc_fma, lc_bytes = 0.0, 0.0
+        try:
+            lc_sweep = local_corr_flow_sweep(dev, args.precision)
+        except Exception as exc:
+            lc_sweep = {"error": f"{type(exc).__name__}: {exc}"[:200]}
         esz = 4 if args.precision.startswith("fp32") else 2
         for res, scales in ((COARSE, arch.SCALES), (UPSAMPLE, arch.UPSAMPLE_SCALES)):
             for sc in scales:
@@ -471,6 +527,7 @@ def run_ours(args):
                           "peak_source": "nominal: 148 SMs x 128 fp32 FMA/clk x 1.9 GHz (no measured fp32 figure in MEASURED_PEAKS.json)",
                           "hbm_achieved_gbs": lc_bytes / (lc_ms / 1e3) / 1e9, "hbm_frac": lc_bytes / (lc_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
                           "ms_per_step": lc_ms,
+                          "flow_sweep": lc_sweep, "flow_sweep_hbm_frac": ({k: round(v["hbm_gbs"] / peaks["hbm_gbs"], 4) for k, v in lc_sweep.items()} if lc_sweep and "error" not in lc_sweep else None),
                           "note": "the windows of neighbouring pixels overlap, so f1 is served from L1/L2 (ncu: 3-50 MB of DRAM reads per launch); "
                                   "the limiter is CUDA-core instruction issue (8 FMA per 21 instructions), not HBM: see DESIGN.md"})
         cpu = None

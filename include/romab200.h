@@ -298,6 +298,7 @@ typedef struct {
     const float* values; int64_t n; int32_t k; int32_t batch; int64_t stride; uint64_t seed; int32_t transform; float param;
     int32_t* out_idx; float* out_weights; float* keys;
     void* scratch;   /* batch * 2056 * 4 bytes: histograms and selection state (cleared inside the call) */
+    const uint64_t* seed_dev;   /* optional: the seed is read from this DEVICE word instead of `seed` (CUDA-graph replays with fresh seeds) */
 } rb_sample_args;
 int romab200_weighted_sample(const rb_sample_args* args, void* stream);
 

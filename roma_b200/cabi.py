@@ -132,7 +132,7 @@ _FIELD_DTYPES = {
     "rb_resize_args": {"in": _F32, "out": _F32},
     "rb_match_epilogue_args": {"state": _F32, "coarse_state": _F32, "warp": _F32, "cert": _F32, "grid_x": _F32, "grid_y": _F32},
     "rb_kde_args": {"x": _F32, "density": _F32},
-    "rb_sample_args": {"values": _F32, "out_idx": torch.int32, "out_weights": _F32, "keys": _F32, "scratch": torch.int32},
+    "rb_sample_args": {"values": _F32, "out_idx": torch.int32, "out_weights": _F32, "keys": _F32, "scratch": torch.int32, "seed_dev": torch.int64},
 }
 
 

@@ -814,9 +814,10 @@ extern "C" int romab200_refiner_prologue(const rb_refiner_prologue_args* a, void
     const int es = a->dtype == RB_F32 ? 4 : 2;
     p.vec_ok = (a->ldf * es) % 16 == 0 && (a->ldd * es) % 16 == 0 && ((uintptr_t)a->feat) % 16 == 0 && ((uintptr_t)a->d) % 16 == 0;
     int64_t pixels = (int64_t)a->D * a->h * a->w;
-    if (a->radius == 0 && 2 * a->cf + a->emb <= 32 && a->ldd <= 32 && p.vec_ok && a->dtype != RB_F32) {
-        unsigned g = (unsigned)((pixels + 255) / 256);
-        if (a->dtype == RB_F16) rb::launch_pdl(refiner_prologue_small_kernel<__half>, dim3(g), dim3(256), 0, st, p);
+    if (a->radius == 0 && 2 * a->cf + a->emb <= 32 && a->ldd <= 32 && p.vec_ok) {
+        unsigned g = (unsigned)((pixels + 255) / 256);      // thin stride-1 maps: one thread per pixel
+        if (a->dtype == RB_F32) rb::launch_pdl(refiner_prologue_small_kernel<float>, dim3(g), dim3(256), 0, st, p);
+        else if (a->dtype == RB_F16) rb::launch_pdl(refiner_prologue_small_kernel<__half>, dim3(g), dim3(256), 0, st, p);
         else rb::launch_pdl(refiner_prologue_small_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, st, p);
         return check_launch("refiner_prologue_small");
     }

@@ -58,9 +58,10 @@ __device__ __forceinline__ void flush_hist(uint32_t* smem_hist, uint32_t* gh, in
 }
 
 // pass 0: keys (grid-wide) + histogram of bits [31:21]
-__global__ void __launch_bounds__(SMP_THREADS) sample_keys_kernel(const float* __restrict__ values, int64_t n, int64_t stride, uint64_t seed, int transform, float param,
-                                                                  float* __restrict__ keys_ws, uint32_t* __restrict__ scratch) {
+__global__ void __launch_bounds__(SMP_THREADS) sample_keys_kernel(const float* __restrict__ values, int64_t n, int64_t stride, uint64_t seed, const uint64_t* __restrict__ seed_dev,
+                                                                  int transform, float param, float* __restrict__ keys_ws, uint32_t* __restrict__ scratch) {
     rb::pdl_wait();
+    if (seed_dev) seed = *seed_dev;
     __shared__ uint32_t hist[SMP_BINS];
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < SMP_BINS; i += SMP_THREADS) hist[i] = 0;
@@ -177,7 +178,7 @@ extern "C" int romab200_weighted_sample(const rb_sample_args* a, void* stream) {
     if (gx > 592) gx = 592;
     if (gx < 1) gx = 1;
     const dim3 grid(gx, a->batch);
-    rb::launch_pdl(sample_keys_kernel, grid, dim3(SMP_THREADS), 0, st, a->values, a->n, stride, a->seed, a->transform, a->param, a->keys, scratch);
+    rb::launch_pdl(sample_keys_kernel, grid, dim3(SMP_THREADS), 0, st, a->values, a->n, stride, a->seed, a->seed_dev, a->transform, a->param, a->keys, scratch);
     if (check_launch("weighted_sample(keys)")) return 1;
     for (int pass = 0; pass < 3; ++pass) {
         rb::launch_pdl(sample_select_kernel, dim3(a->batch), dim3(SMP_THREADS), 0, st, scratch, pass, a->k);
