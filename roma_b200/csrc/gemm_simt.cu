@@ -59,8 +59,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     if (p.lower_only && n0 >= m0 + BM) return;
     const int z = blockIdx.z, z0 = z / p.batch1, z1 = z % p.batch1;
-    const float* __restrict__ A = p.A + z0 * p.sa0 + z1 * p.sa1;
-    const float* __restrict__ B = p.B + z0 * p.sb0 + z1 * p.sb1;
+    // no __restrict__: the GP solve (algo 2) runs P = P L^-T and X = Y L^-1 with C aliasing A.  That is safe because those products
+    // have a single N tile (N <= 128 here) and a CTA reads all of K of its own rows before its epilogue writes them; the operands
+    // are therefore not promised to be read-only (gemm_tc never aliases: its operands are separate split-fp16 scratch pairs).
+    const float* A = p.A + z0 * p.sa0 + z1 * p.sa1;
+    const float* B = p.B + z0 * p.sb0 + z1 * p.sb1;
 
     float acc[TM][TN];
 #pragma unroll

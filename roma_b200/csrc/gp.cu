@@ -619,12 +619,13 @@ static int gp_solve_block128(const rb_gp_solve_args* a, cudaStream_t st) {
     const int64_t ws_stride = (int64_t)nblk * BB * BB;
     float* W = a->W;
     float* ws = (float*)a->workspace;
-    static bool configured = false;
+    static bool configured[64] = {};           // function attributes are per device
+    const int dev = current_device() & 63;
     const size_t smem = (size_t)CB_SMEM_FLOATS * sizeof(float);
-    if (!configured) {
+    if (!configured[dev]) {
         RB_REQUIRE(cudaFuncSetAttribute(chol_block128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
                    "gp_solve: cannot reserve %zu bytes of shared memory", smem);
-        configured = true;
+        configured[dev] = true;
     }
     for (int kb = 0; kb < nblk; ++kb) {
         const int k = kb * BB, bs = n - k < BB ? n - k : BB;
