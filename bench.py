@@ -163,6 +163,34 @@ def local_corr_flow_sweep(dev, precision):
     return out
 
 
+def preprocess_leg(dev, reps=5):
+    """Input preprocessing of the PIL route (utils.py:164-173) for one 12-megapixel frame -> 560x560 and 864x864: the CUDA path (raw bytes
+    H2D + romab200_preprocess_rgb8, CUDA events incl. the copy) beside Pillow + numpy on one host core, and whether the results are the same bits."""
+    import numpy as np
+    from PIL import Image
+    from roma_b200 import preprocess
+    rng = np.random.default_rng(0)
+    pil = Image.fromarray(rng.integers(0, 256, (3000, 4000, 3), dtype=np.uint8), "RGB")
+    pre = preprocess.DevicePreprocessor(dev)
+    sizes = ((COARSE, COARSE), (UPSAMPLE, UPSAMPLE))
+    outs = [pre.resize_normalize(pre.upload(pil), s) for s in sizes]            # warm-up, tables cached
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        raw = pre.upload(pil)
+        for s in sizes:
+            pre.resize_normalize(raw, s)
+    e1.record()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    host = [preprocess.pil_to_normalized(pil, s) for s in sizes]
+    host_ms = (time.perf_counter() - t0) * 1e3
+    same = all(torch.equal(o.cpu(), h) for o, h in zip(outs, host))
+    return {"image": "3000x4000 RGB -> 560x560 + 864x864", "device_ms": e0.elapsed_time(e1) / reps, "pillow_host_ms": host_ms,
+            "bit_exact_vs_pillow": bool(same), "h2d_bytes": 3000 * 4000 * 3}
+
+
 def torch_cuda_baseline(dev, steps=5, warmup=2, with_sample=True):
     """The "existing Blackwell kernels" bar: the same graph through stock PyTorch on this GPU — the oracle's
     torch.nn.functional restatement of the reference with weights and inputs on `cuda`, i.e. cuDNN convolutions, cuBLAS GEMMs, SDPA
@@ -536,6 +564,12 @@ def run_ours(args):
             cpu = {"value": 1.0 / (sum(times) / len(times)), "unit": "pairs/s", "cores": threads, "kind": "port",
                    "sample": f"{len(times)} symmetric pair 560->864 match()" + ("" if args.no_sample else "+sample(10000)") +
                              " through oracle/roma_oracle.py (fp32 restatement of the reference, bit-exact vs it in the build container)"}
+        prep = None
+        if world == 1:
+            try:
+                prep = preprocess_leg(dev)
+            except Exception as exc:
+                prep = {"error": f"{type(exc).__name__}: {exc}"[:200]}
         cfg_name = "configs[1]"
         if args.global_pairs == 64 and world == 8 and args.model == "outdoor":
             cfg_name = "configs[2]"
@@ -565,7 +599,7 @@ def run_ours(args):
                        "l2": "256 MiB buffer written between timed steps; per-step activations also exceed the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_box[0],
                     "ms_per_step": total_ms_e2e / args.steps},
-            "parity": parity, "fast_mode": fast, "gpu_library_baseline": library,
+            "parity": parity, "fast_mode": fast, "gpu_library_baseline": library, "preprocess": prep,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_kernels": extra, "cpu_baseline": cpu,
             "stage_ms_per_step": {k: round(v, 3) for k, v in sorted(stages.items(), key=lambda kv: -kv[1])},
             "gemm_backends": {k: {"tflops": v[0] / (v[1] / 1e3) / 1e12, "ms_per_step": v[1] / args.steps, "launches_per_step": v[2] / args.steps}

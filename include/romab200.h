@@ -302,6 +302,29 @@ typedef struct {
 } rb_sample_args;
 int romab200_weighted_sample(const rb_sample_args* args, void* stream);
 
+/* Image preprocessing in front of match() on the device: RGB uint8 image -> normalised fp32 [3, out_h, out_w]
+ * (get_tuple_transform_ops(resize=(h, w), normalize=True), utils.py:164-173 = PIL.Image.resize((w, h), BICUBIC), /255, ImageNet mean/std;
+ * called at matcher.py:812-815, 855-866).  Bit-exact with Pillow's 8-bit resampling (src/libImaging/Resample.c: 22-bit fixed-point weights,
+ * horizontal pass into a uint8 image, then the vertical pass) and with the reference's fp32 operation order.
+ *
+ * romab200_resample_coeffs is HOST-ONLY arithmetic (no CUDA call, `stream` ignored): the weight table of one axis for in_size -> out_size,
+ * bounds [out_size][2] = (first input sample, count), kk [out_size][ksize] zero-padded rows.  Call it with kk = bounds = NULL to get *ksize
+ * first.  The tables depend on the two sizes only; keep device copies per size pair. */
+typedef struct { int32_t in_size, out_size; int32_t* bounds; int32_t* kk; int32_t* ksize; } rb_resample_coeffs_args;
+int romab200_resample_coeffs(const rb_resample_coeffs_args* args, void* stream);
+
+typedef struct {
+    const uint8_t* in; int64_t ld_in /* bytes per row */; int32_t in_h, in_w;   /* interleaved RGB, 3 bytes per pixel */
+    int32_t out_h, out_w;
+    const int32_t* bounds_x; const int32_t* kk_x; int32_t ksize_x;   /* DEVICE tables for in_w -> out_w (ignored when out_w == in_w) */
+    const int32_t* bounds_y; const int32_t* kk_y; int32_t ksize_y;   /* DEVICE tables for in_h -> out_h (ignored when out_h == in_h) */
+    uint8_t* tmp;      /* in_h * out_w * 3 bytes: the horizontally resampled image (unused when out_w == in_w) */
+    uint8_t* out_u8;   /* optional [out_h, out_w, 3]: the resized 8-bit image, what PIL.Image.resize returns */
+    float* out;        /* optional [3, out_h, out_w]: (u8 / 255 - mean) / std */
+    float mean[3]; float std[3];
+} rb_preprocess_args;
+int romab200_preprocess_rgb8(const rb_preprocess_args* args, void* stream);
+
 /* transpose a batched strided 2-D matrix: dst[b][c][r] = src[b][r][c]  (V^T for the PV product) */
 typedef struct {
     const void* src; void* dst; int32_t rows, cols; int64_t lds, ldd; int32_t batch0, batch1;

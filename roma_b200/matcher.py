@@ -19,7 +19,7 @@ from PIL import Image
 
 from . import cabi
 from .engine import Engine
-from .preprocess import check_input, pil_to_normalized
+from .preprocess import DevicePreprocessor, check_input
 
 
 class RegressionMatcher:
@@ -39,6 +39,7 @@ class RegressionMatcher:
         self.device_sampler = True      # sample(): weighted sampling without replacement in one kernel per draw (False: torch.multinomial)
         self.use_cuda_graph = True      # replay the whole device side of match() as one CUDA graph per input shape
         self._graphs = {}
+        self._pre = None
         self._sample_state = {}         # static buffers + CUDA graph of the device sampler, per (n, num, mode)
         self.graph_launches = 0         # kernels launched through graph replays (cabi.kernel_launches counts eager ones)
 
@@ -96,6 +97,11 @@ class RegressionMatcher:
                                         keep_states=True)
         return self._states_to_corresps(states)
 
+    def _preprocessor(self) -> DevicePreprocessor:
+        if self._pre is None:
+            self._pre = DevicePreprocessor(self.engine.device)
+        return self._pre
+
     @torch.inference_mode()
     def match(self, im_A_input, im_B_input, *args, im_A_high_res=None, im_B_high_res=None, batched=True, device=None):
         """Dense warp and certainty (matcher.py:779-934).  Returns (warp [b,H,W*(2 if symmetric),4] fp32 in
@@ -114,9 +120,12 @@ class RegressionMatcher:
         scale_factor = math.sqrt(hs * ws / (560 ** 2))
         pil_route = isinstance(im_A, Image.Image) and isinstance(im_B, Image.Image)
         if pil_route:
+            # raw RGB bytes go up once per image; Pillow's bicubic resize + normalisation run on the device (csrc/preprocess.cu)
             b = 1
-            a_t = pil_to_normalized(im_A, (hs, ws))[None]
-            b_t = pil_to_normalized(im_B, (hs, ws))[None]
+            pre = self._preprocessor()
+            raw_a, raw_b = pre.upload(im_A), pre.upload(im_B)
+            a_t = pre.resize_normalize(raw_a, (hs, ws))[None]
+            b_t = pre.resize_normalize(raw_b, (hs, ws))[None]
         elif isinstance(im_A, torch.Tensor) and isinstance(im_B, torch.Tensor):
             b, c, h, w = im_A.shape
             b, c, h2, w2 = im_B.shape
@@ -132,14 +141,13 @@ class RegressionMatcher:
         if self.upsample_preds:
             hs, ws = self.upsample_res
             if im_A_high_res is None and im_B_high_res is None:
-                if isinstance(im_A_input, (str, os.PathLike)):
-                    hi_a, hi_b = Image.open(im_A_input).convert("RGB"), Image.open(im_B_input).convert("RGB")
-                else:
+                # the reference re-opens / re-uses the same two images here (matcher.py:855-866): same bytes, already on the device
+                if not isinstance(im_A_input, (str, os.PathLike)):
                     assert isinstance(im_A_input, Image.Image), f"Unsupported input type: {type(im_A_input)=}"
                     assert isinstance(im_B_input, Image.Image), f"Unsupported input type: {type(im_B_input)=}"
-                    hi_a, hi_b = im_A_input, im_B_input
-                a_h = pil_to_normalized(hi_a, (hs, ws))[None]
-                b_h = pil_to_normalized(hi_b, (hs, ws))[None]
+                assert pil_route, "upsample_preds without high-res tensors needs path or PIL inputs"
+                a_h = pre.resize_normalize(raw_a, (hs, ws))[None]
+                b_h = pre.resize_normalize(raw_b, (hs, ws))[None]
             elif im_A_high_res is not None and im_B_high_res is not None:
                 a_h, b_h = im_A_high_res, im_B_high_res
             else:
