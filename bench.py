@@ -167,6 +167,7 @@ def preprocess_leg(dev, reps=5):
     """Input preprocessing of the PIL route (utils.py:164-173) for one 12-megapixel frame -> 560x560 and 864x864: the CUDA path (raw bytes
     H2D + romab200_preprocess_rgb8, CUDA events incl. the copy) beside Pillow + numpy on one host core, and whether the results are the same bits."""
     import numpy as np
+    import torch
     from PIL import Image
     from roma_b200 import preprocess
     rng = np.random.default_rng(0)

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(DwCfg<TIN>::THREADS) dwconv5x5_relu_tma_kernel
     constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, TH = Cfg::TH, NW = Cfg::NWARPS;
     constexpr bool F32IN = sizeof(TIN) == 4;
     extern __shared__ uint8_t dsm_raw[];
-    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsm_raw) + 127) & ~uintptr_t(127));
+    uint8_t* ring = dsm_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(dsm_raw) & 127u)) & 127u);   // offset on the array: keeps ld.shared
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(192, 1) flash_attn_kernel(const __grid_constan
     using Cfg = FaCfg<D>;
     constexpr int STAGES = Cfg::STAGES, BQ = Cfg::BQ, BKV = Cfg::BKV, DB = D / 64;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);   // offset on the array: keeps ld/st.shared
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + Cfg::Q_BYTES;
     uint8_t* sV = sK + STAGES * Cfg::KV_BYTES;
@@ -330,6 +330,11 @@ __global__ void __launch_bounds__(192, 1) flash_attn_kernel(const __grid_constan
 //         (1.5e-11 in units of p) is irrelevant.
 //   out  = O' / (2048 l) written as an RB_F16S pair for the projection GEMM.
 // Warp roles and barriers are those of flash_attn_kernel above.
+//
+// HALVES = 2 runs the softmax with TWO threads per query row (8 softmax warps, two per scheduler instead of one): thread h of a row owns
+// keys [32h, 32h + 32) of every key tile with its own running maximum / sum AND its own output accumulator O_h (the PV MMAs of k-steps
+// 0-1 go to O_0, of k-steps 2-3 to O_1: same MMA count), so no per-tile exchange between the two threads is needed; the two partial
+// results are merged once at the end, out = (O_0 2^(m_0 - m) + O_1 2^(m_1 - m)) / (2048 (l_0 2^(m_0 - m) + l_1 2^(m_1 - m))).
 // ================================================================================================================
 struct FaSplitParams {
     void* out_hi; void* out_lo; int64_t ldo;
@@ -344,17 +349,18 @@ struct FaSplitCfg {
     static constexpr int STAGE_BYTES = 4 * KV_BYTES;        // K_hi, K_lo, V_hi, V_lo
     static constexpr int P_BYTES = BQ * BKV * 2;            // one of the three probability operands
     static constexpr int SMEM = 2 * Q_BYTES + STAGES * STAGE_BYTES + 3 * P_BYTES + 1024 + 256;
-    static constexpr int TMEM_COLS = 512;                   // S: 2 stages x (64 main + 64 cross), O: 64  (power of two >= 320)
+    static constexpr int TMEM_COLS = 512;                   // S: 2 stages x (64 main + 64 cross), O: 64 per key half  (power of two >= 384)
 };
 
-__global__ void __launch_bounds__(192, 1) flash_attn_split_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                                                                   const FaSplitParams p) {
+template <int HALVES>
+__global__ void __launch_bounds__(64 + 128 * HALVES, 1) flash_attn_split_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                                                                                 const FaSplitParams p) {
     rb::pdl_wait();
     using namespace fa;
     using Cfg = FaSplitCfg;
     constexpr int STAGES = Cfg::STAGES, BQ = Cfg::BQ, BKV = Cfg::BKV, D = Cfg::D;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);   // offset on the array: keeps ld/st.shared
     uint8_t* sQh = smem;
     uint8_t* sQl = sQh + Cfg::Q_BYTES;
     uint8_t* sKV = sQl + Cfg::Q_BYTES;                        // per stage: K_hi | K_lo | V_hi | V_lo
@@ -376,8 +382,8 @@ __global__ void __launch_bounds__(192, 1) flash_attn_split_kernel(const __grid_c
     if (warp == 0 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
-        mbar_init(p_ready, 4);
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4 * HALVES); }
+        mbar_init(p_ready, 4 * HALVES);
         mbar_init(pv_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -387,7 +393,7 @@ __global__ void __launch_bounds__(192, 1) flash_attn_split_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_S = tmem_base;              // stage s: main at s * 128, cross at s * 128 + 64
-    const uint32_t tmem_O = tmem_base + 256;        // columns [256, 320)
+    const uint32_t tmem_O = tmem_base + 256;        // columns [256, 320): O (HALVES = 1) or O_0; [320, 384): O_1
 
     if (warp == 0) {
         // ===== TMA producer (boxes of 64 rows x 64 columns; the 128-query tile is two boxes per plane) =====
@@ -451,30 +457,36 @@ __global__ void __launch_bounds__(192, 1) flash_attn_split_kernel(const __grid_c
                     const uint64_t pth = smem_desc(p_addr + k * 32, 16, 1024), ptl = smem_desc(p_addr + Cfg::P_BYTES + k * 32, 16, 1024);
                     const uint64_t ph = smem_desc(p_addr + 2 * Cfg::P_BYTES + k * 32, 16, 1024);
                     const uint64_t vh = smem_desc(vh_addr + k * 2048, BKV * 128, 1024), vl = smem_desc(vl_addr + k * 2048, BKV * 128, 1024);
-                    umma_f16(tmem_O, pth, vh, idesc_o, (j | k) != 0);
-                    umma_f16(tmem_O, ptl, vh, idesc_o, 1u);
-                    umma_f16(tmem_O, ph, vl, idesc_o, 1u);
+                    // HALVES = 2: keys [0, 32) of the tile (k-steps 0, 1) accumulate into O_0, keys [32, 64) into O_1
+                    const uint32_t t_o = HALVES == 2 ? tmem_O + (uint32_t)(k >> 1) * 64 : tmem_O;
+                    const uint32_t acc = HALVES == 2 ? (uint32_t)((j != 0) || (k & 1)) : (uint32_t)((j | k) != 0);
+                    umma_f16(t_o, pth, vh, idesc_o, acc);
+                    umma_f16(t_o, ptl, vh, idesc_o, 1u);
+                    umma_f16(t_o, ph, vl, idesc_o, 1u);
                 }
                 umma_commit(&kv_empty[s]);
                 umma_commit(pv_done);
             }
         }
     } else {
-        // ===== softmax / correction / epilogue: one thread per query row =====
-        const int q = warp & 3;
+        // ===== softmax / correction / epilogue: HALVES threads per query row, each on KW = 64 / HALVES keys of every tile =====
+        constexpr int KW = BKV / HALVES;
+        const int q = warp & 3;                                  // TMEM lane quadrant of this warp
+        const int half = HALVES == 2 ? (warp - 2) >> 2 : 0;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t my_O = tmem_O + (uint32_t)half * 64;
         float m_run = -INFINITY, l_run = 0.f;
         for (int j = 0; j < ntiles; ++j) {
             mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
-            float sc[64];
+            float sc[KW];
             {
                 float cr[32];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    tmem_ld32(tmem_S + lane_addr + (j & 1) * 128 + c * 32, sc + c * 32);
-                    tmem_ld32(tmem_S + lane_addr + (j & 1) * 128 + 64 + c * 32, cr);
+                for (int c = 0; c < KW / 32; ++c) {
+                    tmem_ld32(tmem_S + lane_addr + (j & 1) * 128 + half * KW + c * 32, sc + c * 32);
+                    tmem_ld32(tmem_S + lane_addr + (j & 1) * 128 + 64 + half * KW + c * 32, cr);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) sc[c * 32 + i] = fmaf(cr[i], 1.0f / 2048.0f, sc[c * 32 + i]);
                 }
@@ -482,14 +494,16 @@ __global__ void __launch_bounds__(192, 1) flash_attn_split_kernel(const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[j & 1]);
-            const int valid = min(BKV, p.N - j * BKV);
+            const int valid = min(BKV, p.N - j * BKV) - half * KW;
             float m_new = m_run;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
+            for (int i = 0; i < KW; ++i) {
                 sc[i] = i < valid ? sc[i] * p.scale_log2 : -INFINITY;
                 m_new = fmaxf(m_new, sc[i]);
             }
-            const float alpha = ex2(m_run - m_new);           // 0 on the first tile (m_run = -inf)
+            // a key half that has not seen a valid key yet (N < 33 only) keeps m = -inf: use 0 as the reference so that p = 0, alpha = 0
+            const float m_ref = m_new == -INFINITY ? 0.f : m_new;
+            const float alpha = ex2(m_run - m_ref);           // 0 on the first tile (m_run = -inf)
             if (j > 0) {
                 mbar_wait(pv_done, (j - 1) & 1);              // PV_{j-1} retired: O is stable, the P buffers are free
                 tc_fence_after();
@@ -497,10 +511,10 @@ __global__ void __launch_bounds__(192, 1) flash_attn_split_kernel(const __grid_c
 #pragma unroll
                     for (int c = 0; c < D / 32; ++c) {
                         float o[32];
-                        tmem_ld32(tmem_O + lane_addr + c * 32, o);
+                        tmem_ld32(my_O + lane_addr + c * 32, o);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) o[i] *= alpha;
-                        tmem_st32(tmem_O + lane_addr + c * 32, o);
+                        tmem_st32(my_O + lane_addr + c * 32, o);
                     }
                 }
             }
@@ -508,18 +522,18 @@ __global__ void __launch_bounds__(192, 1) flash_attn_split_kernel(const __grid_c
             // P rows -> K-major SW128 (one 64-key atom): 16-byte chunk c' = (key / 8) XOR (row % 8)
             uint8_t* prow = sP + row * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < KW / 8; ++c) {
                 __half pth[8], ptl[8], ph[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float pv = ex2(sc[c * 8 + e] - m_new);
+                    const float pv = ex2(sc[c * 8 + e] - m_ref);
                     lsum += pv;
                     const float pt = pv * 2048.0f;
                     pth[e] = __float2half_rn(pt);
                     ptl[e] = __float2half_rn(pt - __half2float(pth[e]));
                     ph[e] = __float2half_rn(pv);
                 }
-                const int cc = c ^ (row & 7);
+                const int cc = (c + half * (KW / 8)) ^ (row & 7);
                 *reinterpret_cast<uint4*>(prow + cc * 16) = *reinterpret_cast<uint4*>(pth);
                 *reinterpret_cast<uint4*>(prow + Cfg::P_BYTES + cc * 16) = *reinterpret_cast<uint4*>(ptl);
                 *reinterpret_cast<uint4*>(prow + 2 * Cfg::P_BYTES + cc * 16) = *reinterpret_cast<uint4*>(ph);
@@ -534,20 +548,46 @@ __global__ void __launch_bounds__(192, 1) flash_attn_split_kernel(const __grid_c
         mbar_wait(pv_done, (ntiles - 1) & 1);
         tc_fence_after();
         const int qi = q0 + row;
-        const float inv = 1.0f / (l_run * 2048.0f);
         const int64_t o_off = ((int64_t)img * p.N + qi) * p.ldo + head * D;
+        if constexpr (HALVES == 1) {
+            const float inv = 1.0f / (l_run * 2048.0f);
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
-            float o[32];
-            tmem_ld32(tmem_O + lane_addr + c * 32, o);
+            for (int c = 0; c < D / 32; ++c) {
+                float o[32];
+                tmem_ld32(tmem_O + lane_addr + c * 32, o);
+                if (qi < p.N) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        __half hi[8], lo[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) split_f16s(o[g * 8 + e] * inv, hi[e], lo[e]);
+                        *reinterpret_cast<uint4*>((__half*)p.out_hi + o_off + c * 32 + g * 8) = *reinterpret_cast<uint4*>(hi);
+                        *reinterpret_cast<uint4*>((__half*)p.out_lo + o_off + c * 32 + g * 8) = *reinterpret_cast<uint4*>(lo);
+                    }
+                }
+            }
+        } else {
+            // merge the two key halves: (m, l) of both through shared memory (the P buffers are free after the last PV), then thread h of a
+            // row writes output columns [32h, 32h + 32) from O_0 and O_1
+            float2* ml = reinterpret_cast<float2*>(sP);
+            ml[half * BQ + row] = make_float2(m_run, l_run);
+            asm volatile("bar.sync 1, 256;" ::: "memory");                 // the 8 softmax warps only
+            const float2 a0 = ml[row], a1 = ml[BQ + row];
+            const float m = fmaxf(a0.x, a1.x);                             // finite: key half 0 always holds a valid key
+            const float w0 = ex2(a0.x - m), w1 = ex2(a1.x - m);
+            const float inv = 1.0f / ((a0.y * w0 + a1.y * w1) * 2048.0f);
+            const float s0 = w0 * inv, s1 = w1 * inv;
+            float o0[32], o1[32];
+            tmem_ld32(tmem_O + lane_addr + half * 32, o0);
+            tmem_ld32(tmem_O + 64 + lane_addr + half * 32, o1);
             if (qi < p.N) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     __half hi[8], lo[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) split_f16s(o[g * 8 + e] * inv, hi[e], lo[e]);
-                    *reinterpret_cast<uint4*>((__half*)p.out_hi + o_off + c * 32 + g * 8) = *reinterpret_cast<uint4*>(hi);
-                    *reinterpret_cast<uint4*>((__half*)p.out_lo + o_off + c * 32 + g * 8) = *reinterpret_cast<uint4*>(lo);
+                    for (int e = 0; e < 8; ++e) split_f16s(fmaf(o0[g * 8 + e], s0, o1[g * 8 + e] * s1), hi[e], lo[e]);
+                    *reinterpret_cast<uint4*>((__half*)p.out_hi + o_off + half * 32 + g * 8) = *reinterpret_cast<uint4*>(hi);
+                    *reinterpret_cast<uint4*>((__half*)p.out_lo + o_off + half * 32 + g * 8) = *reinterpret_cast<uint4*>(lo);
                 }
             }
         }
@@ -616,10 +656,14 @@ extern "C" int romab200_flash_attn(const rb_flash_attn_args* a, void* stream) {
         r = enc(&map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(a->qkv_lo), dims, strides, box64, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         RB_REQUIRE(r == CUDA_SUCCESS, "flash_attn: cuTensorMapEncodeTiled (lo plane) failed with %d", (int)r);
+        // ROMAB200_FA_HALVES = 1 | 2: softmax threads per query row of the split kernel (see the kernel's header)
+        const char* halves_env = getenv("ROMAB200_FA_HALVES");      // read per call: tests switch it inside one process
+        const int halves = halves_env && atoi(halves_env) == 2 ? 2 : 1;
         static bool configured[64] = {};
         const int dev = current_device() & 63;
         if (!configured[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(flash_attn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FaSplitCfg::SMEM);
+            cudaError_t e = cudaFuncSetAttribute(flash_attn_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FaSplitCfg::SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_attn_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FaSplitCfg::SMEM);
             RB_REQUIRE(e == cudaSuccess, "flash_attn: cannot set %d bytes of dynamic shared memory: %s", FaSplitCfg::SMEM, cudaGetErrorString(e));
             configured[dev] = true;
         }
@@ -627,7 +671,8 @@ extern "C" int romab200_flash_attn(const rb_flash_attn_args* a, void* stream) {
         sp.out_hi = a->out; sp.out_lo = a->out_lo; sp.ldo = a->ld_out; sp.N = a->n_tokens; sp.heads = a->heads; sp.dim = dim;
         sp.scale_log2 = 1.4426950408889634f / sqrtf((float)a->head_dim);
         dim3 grid((a->n_tokens + FaSplitCfg::BQ - 1) / FaSplitCfg::BQ, a->heads, a->batch);
-        rb::launch_pdl(flash_attn_split_kernel, dim3(grid), dim3(192), FaSplitCfg::SMEM, st, map_hi, map_lo, sp);
+        if (halves == 2) rb::launch_pdl(flash_attn_split_kernel<2>, dim3(grid), dim3(320), FaSplitCfg::SMEM, st, map_hi, map_lo, sp);
+        else rb::launch_pdl(flash_attn_split_kernel<1>, dim3(grid), dim3(192), FaSplitCfg::SMEM, st, map_hi, map_lo, sp);
         return check_launch("flash_attn_split");
     }
     FaParams p;

@@ -462,7 +462,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
     constexpr int OFF_A_LO = A_BYTES, OFF_B = Cfg::NOPS * A_BYTES, OFF_B_LO = Cfg::NOPS * A_BYTES + B_BYTES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);   // offset on the array: keeps ld/st.shared
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;       // [2]
@@ -685,7 +685,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
     constexpr int OFF_A_LO = A_BYTES, OFF_B = Cfg::NOPS * A_BYTES, OFF_B_LO = Cfg::NOPS * A_BYTES + B_BYTES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);   // offset on the array: keeps ld/st.shared
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;       // [2]
@@ -928,6 +928,7 @@ static int launch_tc(const TcMaps& maps, TcParams& p, int zdim, cudaStream_t st)
 }
 
 // 0: never, 1 (default): when profitable, 2: whenever legal (tests).  Environment variable ROMAB200_GEMM_PAIR.
+static int wave_rule() { static const int m = [] { const char* e = getenv("ROMAB200_GEMM_WAVE"); return e ? atoi(e) : 1; }(); return m; }
 static int pair_mode() { static const int m = [] { const char* e = getenv("ROMAB200_GEMM_PAIR"); return e ? atoi(e) : 1; }(); return m; }
 
 template <int BN, bool SPLIT>
@@ -1009,6 +1010,14 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
     // (the threshold is in tiles: below ~100 wide tiles less than 2/3 of the SMs would have work; above it the wider tile wins
     // because these shapes are bound by L2 -> shared-memory operand traffic, which a 128-wide tile raises by a third)
     if (BN > 128 && ((int64_t)((a->M + 127) / 128) * ((a->N + BN - 1) / BN) * zdim) < 100) BN = 128;
+    // CTA-pair candidates: all tiles of a launch take the same time, so the launch costs ceil(tiles / SM pairs) waves of a tile whose time
+    // grows with BN.  When the 256-wide choice ends in a mostly empty last wave, 192-wide tiles finish earlier (ViT qkv, 3202 x 3072:
+    // 156 tiles = 3 waves of 256 columns against 208 tiles = 3 waves of 192); a 5 % handicap keeps the wider tile on ties.
+    if (!a->trans_b && BN == 256 && pair_mode() && wave_rule()) {
+        const long long mt = (long long)((a->M + 255) / 256) * zdim, units = sm_count() / 2 > 0 ? sm_count() / 2 : 1;
+        auto cost = [&](int bn) { const long long t = mt * ((a->N + bn - 1) / bn); return (t + units - 1) / units * bn; };
+        if (mt * ((a->N + 255) / 256) >= 40 && cost(192) * 21 < cost(256) * 20) BN = 192;
+    }
     {   // experiments: ROMAB200_GEMM_BN forces the tile width of the [N,K] layouts when it is one of the instantiated widths
         static const int force_bn = [] { const char* e = getenv("ROMAB200_GEMM_BN"); return e ? atoi(e) : 0; }();
         if (force_bn && !a->trans_b && (force_bn == 32 || force_bn == 64 || force_bn == 128 || force_bn == 144 || force_bn == 192 || force_bn == 256)) BN = force_bn;

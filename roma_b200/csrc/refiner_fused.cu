@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) refiner_block_c144_kernel(const
     rb::pdl_wait();
     using namespace fz;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);   // offset on the array: keeps ld/st.shared
     uint8_t* sA = smem;
     uint8_t* sB = sA + FZ_A_BYTES;
     uint8_t* sIn = sB + FZ_B_BYTES;

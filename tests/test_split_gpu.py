@@ -148,10 +148,13 @@ def test_split_attention_chain(d, N):
     assert rel_err(O.join(), ref_o) < 3e-6
 
 
-@pytest.mark.parametrize("N,scale", [(203, 0.7), (1601, 0.7), (128, 3.0), (64, 0.05), (1, 1.0)])
-def test_split_flash_attention(N, scale):
+@pytest.mark.parametrize("halves", [1, 2])
+@pytest.mark.parametrize("N,scale", [(203, 0.7), (1601, 0.7), (128, 3.0), (64, 0.05), (1, 1.0), (33, 1.0), (97, 0.7)])
+def test_split_flash_attention(N, scale, halves, monkeypatch):
     """Fused split-fp16 attention (head_dim 64) against float64 SDPA: fp32-class, incl. ragged last key tile, peaked
-    (scale 3) and flat (scale 0.05) score distributions."""
+    (scale 3) and flat (scale 0.05) score distributions; with one and with two softmax threads per query row
+    (ROMAB200_FA_HALVES: the second key half of a tile may be empty -- N = 1, 33, 97)."""
+    monkeypatch.setenv("ROMAB200_FA_HALVES", str(halves))
     Bn, H, d = 2, 3, 64
     dim = H * d
     qkv32 = rnd(Bn * N, 3 * dim, seed=1, scale=scale)
