@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 validation call: full GPU suite, smoke, default bench (all legs), A/B of the two new knobs, launch list and targeted ncu captures
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 900 -x > gpurun_out/pytest_gpu_full.log 2>&1; tail -n 12 gpurun_out/pytest_gpu_full.log
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 900 > gpurun_out/pytest_gpu_full.log 2>&1; tail -n 12 gpurun_out/pytest_gpu_full.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -n 4 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_final_n1.json 2> gpurun_out/bench_final_n1.err; tail -n 3 gpurun_out/bench_final_n1.err
 ROMAB200_FA_HALVES=2 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-library-baseline --no-fast-mode > gpurun_out/bench_halves2.json 2> gpurun_out/bench_halves2.err
