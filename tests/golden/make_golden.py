@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from roma_b200 import synthetic  # noqa: E402
-from romatch import roma_outdoor  # noqa: E402  (the reference)
+from romatch import roma_indoor, roma_outdoor  # noqa: E402  (the reference)
 
 
 def checksum(t):
@@ -28,9 +28,9 @@ def checksum(t):
     return np.array([t.sum().item(), t.abs().sum().item(), (t * t).sum().item()])
 
 
-def run(name, coarse, up, symmetric=True, upsample_preds=True, batch=1, seed=1, step=1, hooks=True, pil=False):
+def run(name, coarse, up, symmetric=True, upsample_preds=True, batch=1, seed=1, step=1, hooks=True, pil=False, factory=roma_outdoor):
     mw, dw = synthetic.make_weights(0)
-    model = roma_outdoor("cpu", weights=mw, dinov2_weights=dw, coarse_res=coarse,
+    model = factory("cpu", weights=mw, dinov2_weights=dw, coarse_res=coarse,
                          upsample_res=up if up else coarse, symmetric=symmetric,
                          upsample_preds=upsample_preds, use_custom_corr=False)
     out = {}
@@ -76,6 +76,10 @@ def run(name, coarse, up, symmetric=True, upsample_preds=True, batch=1, seed=1, 
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])                 # optional: names of the fixtures to (re)generate
+
+    if only:
+        _run, run = run, (lambda name, *a, **k: _run(name, *a, **k) if name in only else None)
     run("small_sym_up", 112, 168)
     run("small_nosym_up", 112, 168, symmetric=False, hooks=False)
     run("small_sym_noup", 112, None, upsample_preds=False, hooks=False)
@@ -83,3 +87,5 @@ if __name__ == "__main__":
     run("small_pil_sym_up", 112, 168, pil=True, hooks=False, seed=3)
     run("rect_sym_up", (112, 168), (168, 224), hooks=False, seed=5)
     run("full_sym_up", 560, 864, step=8, hooks=False)
+    run("full_nosym_up", 560, 864, symmetric=False, step=8, hooks=False, seed=2)
+    run("small_indoor_sym_up", 112, 168, hooks=False, seed=9, factory=roma_indoor)

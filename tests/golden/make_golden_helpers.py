@@ -60,6 +60,22 @@ def main():
     out["fb_batched"] = fb2.numpy()
     np.savez_compressed(os.path.join(HERE, "helpers.npz"), **out)
     print({k: v.shape for k, v in out.items()}, "matches:", len(out["kp_inds_A"]), "fb mean:", float(fb.mean()))
+    # visualize_warp (matcher.py:936-989) on CPU: PIL inputs (symmetric and one-directional) and tensor inputs, plus the saved PNG
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from roma_b200 import synthetic
+    import tempfile
+    from PIL import Image
+    im_a, im_b = synthetic.make_pil_pair(11, size_a=(50, 40), size_b=(45, 60))
+    vis = {"vis_sym": ref.visualize_warp(warp, certainty, im_a, im_b, device="cpu").numpy(),
+           "vis_one": ref.visualize_warp(warp[:, :W], certainty[:, :W], im_a, im_b, device="cpu", symmetric=False).numpy()}
+    xa, xb = torch.rand(3, H, W, generator=g), torch.rand(3, H, W, generator=g)
+    vis["x_A"], vis["x_B"] = xa.numpy(), xb.numpy()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "v.png")
+        vis["vis_tensor"] = ref.visualize_warp(warp, certainty, xa, xb, device="cpu", save_path=path).numpy()
+        vis["saved_png"] = np.asarray(Image.open(path))
+    np.savez_compressed(os.path.join(HERE, "helpers_visualize.npz"), **vis)
+    print({k: v.shape for k, v in vis.items()})
 
 
 if __name__ == "__main__":

@@ -64,3 +64,21 @@ def test_conf_from_fb_consistency():
     fb2 = m.conf_from_fb_consistency(torch.stack((a_to_b, grid)), torch.stack((b_to_a, grid)), th=1)
     assert fb2.shape == (2, 24, 32) and torch.equal(fb2, _t("fb_batched"))
     assert fb2[1].min() == 1.0                          # the identity flow is consistent with itself everywhere
+
+
+def test_visualize_warp(tmp_path):
+    """visualize_warp (matcher.py:936-989) against the reference's output: PIL inputs (symmetric / one direction), tensor inputs,
+    and the PNG written through `save_path` (tensor_to_pil, utils.py)."""
+    from PIL import Image
+    from roma_b200 import synthetic
+    V = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "helpers_visualize.npz"))
+    m = _model()
+    warp, cert = _t("warp"), _t("certainty")
+    W = warp.shape[1] // 2
+    im_a, im_b = synthetic.make_pil_pair(11, size_a=(50, 40), size_b=(45, 60))
+    assert torch.equal(m.visualize_warp(warp, cert, im_a, im_b, device="cpu"), torch.from_numpy(V["vis_sym"]))
+    assert torch.equal(m.visualize_warp(warp[:, :W], cert[:, :W], im_a, im_b, device="cpu", symmetric=False), torch.from_numpy(V["vis_one"]))
+    path = str(tmp_path / "v.png")
+    vis = m.visualize_warp(warp, cert, torch.from_numpy(V["x_A"]), torch.from_numpy(V["x_B"]), device="cpu", save_path=path)
+    assert torch.equal(vis, torch.from_numpy(V["vis_tensor"]))
+    assert np.array_equal(np.asarray(Image.open(path)), V["saved_png"])

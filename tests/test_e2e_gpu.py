@@ -208,6 +208,31 @@ def test_match_full_vs_reference_golden(weights, backend):
     model.free_buffers()
 
 
+@pytest.mark.slow
+def test_match_full_one_direction_vs_reference_golden(weights):
+    """560 -> 864 with symmetric=False (one-directional warp, `forward` instead of `forward_symmetric`, matcher.py:831-834)."""
+    g = load_golden("full_nosym_up")
+    model = build(weights, g)
+    A, B, Ah, Bh = synthetic.make_pair(1, 560, 864, int(g["meta"][5]))
+    warp, cert = model.match(A.cuda(), B.cuda(), im_A_high_res=Ah.cuda(), im_B_high_res=Bh.cuda())
+    assert warp.shape == (1, 864, 864, 4)
+    ew, ec = report("full one-direction", warp, cert, g, step=8)
+    assert ew <= TOL and ec <= TOL
+    model.free_buffers()
+
+
+def test_roma_indoor_vs_reference_golden(weights):
+    """`roma_indoor` (BASELINE config 4's factory, model_zoo/__init__.py:64-94) against the reference's roma_indoor."""
+    from roma_b200 import roma_indoor
+    g = load_golden("small_indoor_sym_up")
+    coarse, up, sym, upp, batch, seed, step = (int(v) for v in g["meta"])
+    model = roma_indoor("cuda", weights=weights[0], dinov2_weights=weights[1], coarse_res=coarse, upsample_res=up, amp_dtype=torch.float32)
+    A, B, Ah, Bh = synthetic.make_pair(batch, coarse, up, seed)
+    warp, cert = model.match(A.cuda(), B.cuda(), im_A_high_res=Ah.cuda(), im_B_high_res=Bh.cuda())
+    ew, ec = report("indoor", warp, cert, g)
+    assert ew <= TOL and ec <= TOL
+
+
 @pytest.mark.parametrize("amp", [torch.float16, torch.bfloat16])
 def test_match_fast_mode_small(weights, amp):
     """16-bit tensor-core mode (the reference's CUDA autocast regime).  Two fp16 implementations do not agree to
