@@ -128,7 +128,7 @@ template <int D> struct FaCfg {
     static constexpr int Q_BYTES = BQ * D * 2;
     static constexpr int KV_BYTES = BKV * D * 2;            // one of K, V
     static constexpr int P_BYTES = BQ * BKV * 2;
-    static constexpr int SMEM = Q_BYTES + STAGES * 2 * KV_BYTES + P_BYTES + 1024 + 256;
+    static constexpr int SMEM = Q_BYTES + STAGES * 2 * KV_BYTES + 2 * P_BYTES + 1024 + 256;   // two probability buffers
     static constexpr int TMEM_COLS = 512;                   // S: 2 x 128, O: D  (power of two >= 256 + D)
 };
 
@@ -144,15 +144,15 @@ __global__ void __launch_bounds__(192, 1) flash_attn_kernel(const __grid_constan
     uint8_t* sK = sQ + Cfg::Q_BYTES;
     uint8_t* sV = sK + STAGES * Cfg::KV_BYTES;
     uint8_t* sP = sV + STAGES * Cfg::KV_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::P_BYTES);
     uint64_t* q_full = bars;                  // [1]
     uint64_t* kv_full = bars + 1;             // [STAGES]
     uint64_t* kv_empty = kv_full + STAGES;    // [STAGES]
     uint64_t* s_full = kv_empty + STAGES;     // [2]
     uint64_t* s_empty = s_full + 2;           // [2]
-    uint64_t* p_ready = s_empty + 2;          // [1]
-    uint64_t* pv_done = p_ready + 1;          // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+    uint64_t* p_ready = s_empty + 2;          // [2]  one per probability buffer (tile j uses buffer j & 1)
+    uint64_t* pv_done = p_ready + 2;          // [2]  PV_j retired, committed on pv_done[j & 1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BQ, head = blockIdx.y, img = blockIdx.z;
@@ -161,9 +161,7 @@ __global__ void __launch_bounds__(192, 1) flash_attn_kernel(const __grid_constan
     if (warp == 0 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
-        mbar_init(p_ready, 4);
-        mbar_init(pv_done, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); mbar_init(&p_ready[s], 4); mbar_init(&pv_done[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -219,22 +217,24 @@ __global__ void __launch_bounds__(192, 1) flash_attn_kernel(const __grid_constan
             issue_s(0);
             for (int j = 0; j < ntiles; ++j) {
                 if (j + 1 < ntiles) issue_s(j + 1);
-                mbar_wait(p_ready, j & 1);
+                mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
                 tc_fence_after();
                 const int s = j % STAGES;
                 const uint32_t v_addr = smem_u32(sV + s * Cfg::KV_BYTES);
 #pragma unroll
                 for (int k = 0; k < BKV / 16; ++k) {
-                    const uint32_t a_off = (k >> 2) * (BQ * 128) + (k & 3) * 32;    // P: two 64-key blocks
+                    const uint32_t a_off = (j & 1) * Cfg::P_BYTES + (k >> 2) * (BQ * 128) + (k & 3) * 32;    // P buffer j & 1: two 64-key blocks
                     // V tile: D/64 boxes of [128 keys x 128 B]; 16 keys = 2 swizzle row-groups = 2048 B
                     umma_f16(tmem_O, smem_desc(p_addr + a_off, 16, 1024), smem_desc(v_addr + k * 2048, BKV * 128, 1024), idesc_o, (j | k) != 0);
                 }
                 umma_commit(&kv_empty[s]);
-                umma_commit(pv_done);
+                umma_commit(&pv_done[j & 1]);
             }
         }
     } else {
         // ===== softmax / correction / epilogue: one thread per query row =====
+        // The probabilities are double-buffered, so this loop runs one tile ahead of the PV products: it only waits for PV_{j-2} (its
+        // buffer is free again) and, when a running maximum moved, for PV_{j-1} before rescaling O in TMEM.
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -256,23 +256,22 @@ __global__ void __launch_bounds__(192, 1) flash_attn_kernel(const __grid_constan
                 m_new = fmaxf(m_new, sc[i]);
             }
             const float alpha = ex2(m_run - m_new);           // 0 on the first tile (m_run = -inf)
-            if (j > 0) {
-                mbar_wait(pv_done, (j - 1) & 1);              // PV_{j-1} retired: O is stable, the P buffer is free
+            if (j > 0 && __any_sync(0xffffffffu, m_new > m_run)) {
+                mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // PV_{j-1} (and all before it) retired: O is stable
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, m_new > m_run)) {
 #pragma unroll
-                    for (int c = 0; c < D / 32; ++c) {
-                        float o[32];
-                        tmem_ld32(tmem_O + lane_addr + c * 32, o);
+                for (int c = 0; c < D / 32; ++c) {
+                    float o[32];
+                    tmem_ld32(tmem_O + lane_addr + c * 32, o);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] *= alpha;
-                        tmem_st32(tmem_O + lane_addr + c * 32, o);
-                    }
+                    for (int i = 0; i < 32; ++i) o[i] *= alpha;
+                    tmem_st32(tmem_O + lane_addr + c * 32, o);
                 }
             }
+            if (j >= 2) mbar_wait(&pv_done[j & 1], ((j >> 1) - 1) & 1);   // PV_{j-2} retired: probability buffer j & 1 is free
             float lsum = 0.f;
             // P row -> K-major SW128: block kb = key/64, 16-byte chunk c' = (key%64)/8 XOR (row%8)
-            uint8_t* prow = sP + row * 128;
+            uint8_t* prow = sP + (j & 1) * Cfg::P_BYTES + row * 128;
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 T pk[8];
@@ -290,9 +289,9 @@ __global__ void __launch_bounds__(192, 1) flash_attn_kernel(const __grid_constan
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to UMMA
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_ready);
+            if (lane == 0) mbar_arrive(&p_ready[j & 1]);
         }
-        mbar_wait(pv_done, (ntiles - 1) & 1);
+        mbar_wait(&pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
         tc_fence_after();
         const int qi = q0 + row;
         const float inv = 1.0f / l_run;
@@ -348,7 +347,7 @@ struct FaSplitCfg {
     static constexpr int KV_BYTES = BKV * D * 2;            // one plane of one of K, V
     static constexpr int STAGE_BYTES = 4 * KV_BYTES;        // K_hi, K_lo, V_hi, V_lo
     static constexpr int P_BYTES = BQ * BKV * 2;            // one of the three probability operands
-    static constexpr int SMEM = 2 * Q_BYTES + STAGES * STAGE_BYTES + 3 * P_BYTES + 1024 + 256;
+    static constexpr int SMEM = 2 * Q_BYTES + STAGES * STAGE_BYTES + 2 * 3 * P_BYTES + 1024 + 256;   // two sets of the three probability operands
     static constexpr int TMEM_COLS = 512;                   // S: 2 stages x (64 main + 64 cross), O: 64 per key half  (power of two >= 384)
 };
 
@@ -364,16 +363,17 @@ __global__ void __launch_bounds__(64 + 128 * HALVES, 1) flash_attn_split_kernel(
     uint8_t* sQh = smem;
     uint8_t* sQl = sQh + Cfg::Q_BYTES;
     uint8_t* sKV = sQl + Cfg::Q_BYTES;                        // per stage: K_hi | K_lo | V_hi | V_lo
-    uint8_t* sP = sKV + STAGES * Cfg::STAGE_BYTES;            // Pt_hi | Pt_lo | P_hi
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 3 * Cfg::P_BYTES);
+    uint8_t* sP = sKV + STAGES * Cfg::STAGE_BYTES;            // two buffers of Pt_hi | Pt_lo | P_hi (tile j uses buffer j & 1)
+    constexpr int PSET = 3 * Cfg::P_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * PSET);
     uint64_t* q_full = bars;                  // [1]
     uint64_t* kv_full = bars + 1;             // [STAGES]
     uint64_t* kv_empty = kv_full + STAGES;    // [STAGES]
     uint64_t* s_full = kv_empty + STAGES;     // [2]
     uint64_t* s_empty = s_full + 2;           // [2]
-    uint64_t* p_ready = s_empty + 2;          // [1]
-    uint64_t* pv_done = p_ready + 1;          // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+    uint64_t* p_ready = s_empty + 2;          // [2]  one per probability buffer
+    uint64_t* pv_done = p_ready + 2;          // [2]  PV_j retired, committed on pv_done[j & 1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BQ, head = blockIdx.y, img = blockIdx.z;
@@ -382,9 +382,9 @@ __global__ void __launch_bounds__(64 + 128 * HALVES, 1) flash_attn_split_kernel(
     if (warp == 0 && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4 * HALVES); }
-        mbar_init(p_ready, 4 * HALVES);
-        mbar_init(pv_done, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4 * HALVES); mbar_init(&p_ready[s], 4 * HALVES); mbar_init(&pv_done[s], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -447,15 +447,16 @@ __global__ void __launch_bounds__(64 + 128 * HALVES, 1) flash_attn_split_kernel(
             issue_s(0);
             for (int j = 0; j < ntiles; ++j) {
                 if (j + 1 < ntiles) issue_s(j + 1);
-                mbar_wait(p_ready, j & 1);
+                mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
                 tc_fence_after();
                 const int s = j % STAGES;
+                const uint32_t pj_addr = p_addr + (j & 1) * PSET;
                 const uint32_t vh_addr = smem_u32(sKV + s * Cfg::STAGE_BYTES + 2 * Cfg::KV_BYTES), vl_addr = vh_addr + Cfg::KV_BYTES;
 #pragma unroll
                 for (int k = 0; k < BKV / 16; ++k) {
                     // P operands: 128 rows x 64 keys (one swizzle atom wide), 16 keys = 32 B; V tile [64 keys x 128 B]: 16 keys = 2048 B
-                    const uint64_t pth = smem_desc(p_addr + k * 32, 16, 1024), ptl = smem_desc(p_addr + Cfg::P_BYTES + k * 32, 16, 1024);
-                    const uint64_t ph = smem_desc(p_addr + 2 * Cfg::P_BYTES + k * 32, 16, 1024);
+                    const uint64_t pth = smem_desc(pj_addr + k * 32, 16, 1024), ptl = smem_desc(pj_addr + Cfg::P_BYTES + k * 32, 16, 1024);
+                    const uint64_t ph = smem_desc(pj_addr + 2 * Cfg::P_BYTES + k * 32, 16, 1024);
                     const uint64_t vh = smem_desc(vh_addr + k * 2048, BKV * 128, 1024), vl = smem_desc(vl_addr + k * 2048, BKV * 128, 1024);
                     // HALVES = 2: keys [0, 32) of the tile (k-steps 0, 1) accumulate into O_0, keys [32, 64) into O_1
                     const uint32_t t_o = HALVES == 2 ? tmem_O + (uint32_t)(k >> 1) * 64 : tmem_O;
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(64 + 128 * HALVES, 1) flash_attn_split_kernel(
                     umma_f16(t_o, ph, vl, idesc_o, 1u);
                 }
                 umma_commit(&kv_empty[s]);
-                umma_commit(pv_done);
+                umma_commit(&pv_done[j & 1]);
             }
         }
     } else {
@@ -504,23 +505,24 @@ __global__ void __launch_bounds__(64 + 128 * HALVES, 1) flash_attn_split_kernel(
             // a key half that has not seen a valid key yet (N < 33 only) keeps m = -inf: use 0 as the reference so that p = 0, alpha = 0
             const float m_ref = m_new == -INFINITY ? 0.f : m_new;
             const float alpha = ex2(m_run - m_ref);           // 0 on the first tile (m_run = -inf)
-            if (j > 0) {
-                mbar_wait(pv_done, (j - 1) & 1);              // PV_{j-1} retired: O is stable, the P buffers are free
+            // the probability operands are double-buffered, so this loop runs one tile ahead of the PV products: it only waits for
+            // PV_{j-2} (its buffer is free again) and, when a running maximum moved, for PV_{j-1} before rescaling O in TMEM
+            if (j > 0 && __any_sync(0xffffffffu, m_new > m_run)) {
+                mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // PV_{j-1} (and all before it) retired: O is stable
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, m_new > m_run)) {
 #pragma unroll
-                    for (int c = 0; c < D / 32; ++c) {
-                        float o[32];
-                        tmem_ld32(my_O + lane_addr + c * 32, o);
+                for (int c = 0; c < D / 32; ++c) {
+                    float o[32];
+                    tmem_ld32(my_O + lane_addr + c * 32, o);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] *= alpha;
-                        tmem_st32(my_O + lane_addr + c * 32, o);
-                    }
+                    for (int i = 0; i < 32; ++i) o[i] *= alpha;
+                    tmem_st32(my_O + lane_addr + c * 32, o);
                 }
             }
+            if (j >= 2) mbar_wait(&pv_done[j & 1], ((j >> 1) - 1) & 1);   // PV_{j-2} retired: probability buffer j & 1 is free
             float lsum = 0.f;
             // P rows -> K-major SW128 (one 64-key atom): 16-byte chunk c' = (key / 8) XOR (row % 8)
-            uint8_t* prow = sP + row * 128;
+            uint8_t* prow = sP + (j & 1) * PSET + row * 128;
 #pragma unroll
             for (int c = 0; c < KW / 8; ++c) {
                 __half pth[8], ptl[8], ph[8];
@@ -543,9 +545,9 @@ __global__ void __launch_bounds__(64 + 128 * HALVES, 1) flash_attn_split_kernel(
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to UMMA
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_ready);
+            if (lane == 0) mbar_arrive(&p_ready[j & 1]);
         }
-        mbar_wait(pv_done, (ntiles - 1) & 1);
+        mbar_wait(&pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
         tc_fence_after();
         const int qi = q0 + row;
         const int64_t o_off = ((int64_t)img * p.N + qi) * p.ldo + head * D;
