@@ -111,7 +111,7 @@ def cpu_reference_time(steps, warmup, budget_s=240.0, with_sample=True):
     return times, torch.get_num_threads()
 
 
-def local_corr_flow_sweep(dev, precision):
+def local_corr_flow_sweep(dev, precision, tile_pass=True):
     """The local-correlation prologue kernels alone, on smooth flow (identity + 0.5 pixel of noise: neighbouring pixels share their
     windows) and on random flow (uniform over the image: no sharing, what the seeded synthetic weights produce): ms per launch and the
     compulsory HBM bytes of SURVEY 8d (read f0 + f1 + flow, write the window) per second, for the five launches of one direction pair."""
@@ -146,6 +146,9 @@ def local_corr_flow_sweep(dev, precision):
                 R = dict(emb_w=torch.randn(spec.emb, 2).to(dev), emb_b=torch.randn(spec.emb).to(dev))
                 kw = dict(feat=feat, ldf=ldf, n_img=E, y_shift=1, state=state, d=d, ldd=cp, D=D, h=h, w=w, cf=spec.feat, emb=spec.emb, radius=r, dtype=code,
                           emb_weight=R["emb_w"], emb_bias=R["emb_b"], disp_scale=1.25, grid_x=xs.to(dev), grid_y=ys.to(dev), win_x=wx, win_y=wy)
+                if dt == torch.float32 and tile_pass:       # workspace of the tile-cooperative pass (what the engine passes in the parity mode)
+                    tiles = torch.zeros(D * cabi.prologue_tiles(r, h, w), dtype=torch.uint8, device=dev)
+                    kw.update(tile_done=tiles, tile_done_len=tiles.numel())
                 for _ in range(2):
                     call("romab200_refiner_prologue", "rb_refiner_prologue_args", **kw)
                 ts = []

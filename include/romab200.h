@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ROMAB200_ABI_VERSION 3
+#define ROMAB200_ABI_VERSION 4
 
 enum rb_dtype { RB_F32 = 0, RB_F16 = 1, RB_BF16 = 2, RB_F16S = 3 };
 enum rb_act { RB_ACT_NONE = 0, RB_ACT_RELU = 1, RB_ACT_GELU = 2 };
@@ -203,6 +203,16 @@ typedef struct {
     const float* emb_weight /* [emb][2] */; const float* emb_bias; float disp_scale;
     const float* grid_x; const float* grid_y;   /* linspace(-1+1/w, 1-1/w, w), linspace(-1+1/h, 1-1/h, h) (matcher.py:136-143) */
     const float* win_x; const float* win_y;     /* linspace(-2r/w, 2r/w, 2r+1), linspace(-2r/h, 2r/h, 2r+1) (local_correlation.py:93-103) */
+    /* optional workspace (caller-owned, like every buffer): one byte per tile of the tile-cooperative pass for fp32 maps with a local
+     * correlation (radius 7: 8x2 pixels (x by y), radius 3 / 2: 8x4 pixels per tile; D * ceil(h/Ty) * ceil(w/Tx) tiles).  When given, tiles whose
+     * windows overlap (coherent flow) are produced by one CTA from a shared-memory copy of the union of their windows; the rest by the
+     * per-pixel kernel.  NULL: per-pixel kernel only.  Same results either way up to the summation order of the dot products. */
+    void* tile_done; int32_t tile_done_len;
+    /* optional all-pairs table (radius > 0): corr_table[(item*h*w + p) * ld_corr_table + q] = <x[item, p, :], y[item, q, :]> / sqrt(cf) for every
+     * position q of the other map, e.g. one romab200_gemm per direction at the coarsest scale, where the table is small (h*w = 1600) and the
+     * contraction is the one the GP kernel matrix performs anyway (matcher.py:298-300).  The window dot products then are a gather of
+     * (2r+2)^2 table entries per pixel instead of (2r+2)^2 * cf multiply-adds.  NULL: the dot products are computed here. */
+    const float* corr_table; int64_t ld_corr_table;
 } rb_refiner_prologue_args;
 int romab200_refiner_prologue(const rb_refiner_prologue_args* args, void* stream);
 

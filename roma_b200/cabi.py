@@ -122,7 +122,7 @@ _FIELD_DTYPES = {
     "rb_gp_solve_args": {"W": _F32},
     "rb_cls_args": {"logits": "dtype", "state": _F32},
     "rb_refiner_prologue_args": {"feat": "dtype", "state": _F32, "d": "dtype", "emb_weight": _F32, "emb_bias": _F32, "grid_x": _F32, "grid_y": _F32,
-                                 "win_x": _F32, "win_y": _F32},
+                                 "win_x": _F32, "win_y": _F32, "tile_done": torch.uint8, "corr_table": _F32},
     "rb_local_corr_args": {"f0": "dtype_f", "f1": "dtype_f", "flow": _F32, "out": "dtype_out", "win_x": _F32, "win_y": _F32},
     "rb_local_corr_warp_args": {"f0": _F32, "f1": _F32, "warp": _F32, "out": _F32},
     "rb_dwconv_args": {"in": "dtype", "weight": _F32, "bias": _F32, "out_lo": torch.float16},
@@ -199,6 +199,12 @@ def call(fn_name: str, struct_name: str, **kw) -> None:
     launch_count += 1
     if rc != 0:
         raise RuntimeError(f"{fn_name} failed: {lib.romab200_last_error().decode()}")
+
+
+def prologue_tiles(radius: int, h: int, w: int) -> int:
+    """Tiles per map of the tile-cooperative refiner prologue (`tile_done` bytes per decoder item; include/romab200.h)."""
+    ty = 2 if radius == 7 else 4
+    return ((h + ty - 1) // ty) * ((w + 7) // 8)
 
 
 def kernel_launches() -> int:

@@ -5,7 +5,7 @@
 // certainty logit travel together as a 3-channel fp32 "state" map [D, h, w, 3] = (x, y, logit).
 // All kernels here are gather / streaming kernels (HBM- or L2-bound); one warp per pixel with lanes over
 // channels, so every global access is a contiguous run of the channel vector.
-#include "common.cuh"
+#include "refiner_common.cuh"
 
 namespace rb {
 
@@ -51,13 +51,27 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 template <typename T, int R, typename TO>
 __device__ __forceinline__ void local_corr_warp(const T* __restrict__ f0, const T* __restrict__ f1, int64_t ldf1, float fx, float fy,
                                                 int h, int w, int c, float scale, const float* __restrict__ winx,
-                                                const float* __restrict__ winy, float* __restrict__ dtab, TO* __restrict__ out, int lane) {
-    constexpr int S = 2 * R + 2, P = S * S, K1 = 2 * R + 1, K = K1 * K1;
+                                                const float* __restrict__ winy, float* __restrict__ dtab, TO* __restrict__ out, int lane,
+                                                const float* __restrict__ table_row = nullptr) {
+    constexpr int S = 2 * R + 2, P = S * S;
     constexpr int VN = Vec16<T>::N;
     constexpr int MAXCH = 512 / (32 * VN);      // channel chunks per lane (c <= 512)
     const float cx = ((fx + 1.f) * w - 1.f) * 0.5f, cy = ((fy + 1.f) * h - 1.f) * 0.5f;
     const int bx = (int)floorf(cx) - R, by = (int)floorf(cy) - R;
 
+    if (table_row) {
+        // the dot products of this pixel with EVERY position of the other map already exist (one tensor-core GEMM per direction,
+        // the same contraction as the all-pairs GP kernel at this scale): D is a gather of (2R+2)^2 table entries
+        for (int pl = lane; pl < P; pl += 32) {
+            const int jl = pl / S, il = pl - jl * S;
+            const int xl = bx + il, yl = by + jl;
+            dtab[pl] = (xl >= 0 && xl < w && yl >= 0 && yl < h) ? table_row[yl * w + xl] : 0.f;
+        }
+        __syncwarp();
+        lc_blend_window<R, TO>(dtab, fx, fy, bx, by, h, w, winx, winy, out, lane);
+        __syncwarp();
+        return;
+    }
     float f0r[MAXCH][VN];
 #pragma unroll
     for (int t = 0; t < MAXCH; ++t) {
@@ -119,33 +133,13 @@ __device__ __forceinline__ void local_corr_warp(const T* __restrict__ f0, const 
         if (g * 32 + lane < P) dtab[g * 32 + lane] = tot * scale;
     }
     __syncwarp();
-    for (int k = lane; k < K; k += 32) {
-        int dy = k / K1, dx = k - dy * K1;
-        float xk = fx + winx[dx], yk = fy + winy[dy];
-        float ix = ((xk + 1.f) * w - 1.f) * 0.5f, iy = ((yk + 1.f) * h - 1.f) * 0.5f;
-        float x0 = floorf(ix), y0 = floorf(iy);
-        float wx1 = ix - x0, wx0 = (x0 + 1.f) - ix, wy1 = iy - y0, wy0 = (y0 + 1.f) - iy;
-        int ti = (int)x0 - bx, tj = (int)y0 - by;
-        int ti0 = min(max(ti, 0), S - 1), ti1 = min(max(ti + 1, 0), S - 1);
-        int tj0 = min(max(tj, 0), S - 1), tj1 = min(max(tj + 1, 0), S - 1);
-        float v = dtab[tj0 * S + ti0] * (wx0 * wy0) + dtab[tj0 * S + ti1] * (wx1 * wy0) +
-                  dtab[tj1 * S + ti0] * (wx0 * wy1) + dtab[tj1 * S + ti1] * (wx1 * wy1);
-        out[k] = from_f<TO>(v);
-    }
+    lc_blend_window<R, TO>(dtab, fx, fy, bx, by, h, w, winx, winy, out, lane);
     __syncwarp();
 }
 
 // --------------------------------------------------------------------------------------------------
 // ConvRefiner prologue: d = [x | grid_sample(y, flow) | disp_emb | local_corr]   (matcher.py:132-168)
 // --------------------------------------------------------------------------------------------------
-struct PrologueParams {
-    const void* feat; int64_t ldf; int n_img, y_shift;
-    const float* state; void* d; int64_t ldd;
-    int D, h, w, cf, emb;
-    const float* emb_w; const float* emb_b; float disp_scale;
-    const float* gx; const float* gy; const float* winx; const float* winy;
-    int vec_ok;
-};
 
 // thin maps (stride 1: 9 feature channels, 24 in total): one THREAD per pixel, the whole d row is assembled in
 // registers and written with 16-byte stores (a warp per pixel would leave 3/4 of the lanes idle on 1.5 M pixels)
@@ -215,6 +209,9 @@ __global__ void __launch_bounds__(128) refiner_prologue_kernel(const ProloguePar
     const int item = (int)(pix / hw);
     const int rem = (int)(pix - item * hw);
     const int y = rem / p.w, x = rem - y * p.w;
+    if constexpr (R > 0) {
+        if (p.tile_done && p.tile_done[lc_tile_index<R>(item, y, x, p.h, p.w)]) return;     // written by refiner_prologue_tile_kernel
+    }
     const float fx = p.state[pix * 3 + 0], fy = p.state[pix * 3 + 1];
     const T* feat = (const T*)p.feat;
     const T* xrow = feat + ((int64_t)item * hw + rem) * p.ldf;
@@ -276,7 +273,7 @@ __global__ void __launch_bounds__(128) refiner_prologue_kernel(const ProloguePar
         drow[2 * cf + e] = from_f<T>(p.emb_w[2 * e] * ddx + p.emb_w[2 * e + 1] * ddy + p.emb_b[e]);
     if constexpr (R > 0)
         local_corr_warp<T, R, T>(xrow, yimg, p.ldf, fx, fy, p.h, p.w, cf, rsqrtf((float)cf), p.winx, p.winy, dtab_all[wid],
-                                 drow + 2 * cf + p.emb, lane);
+                                 drow + 2 * cf + p.emb, lane, p.corr_table ? p.corr_table + pix * p.ld_table : nullptr);
 }
 
 // stand-alone local correlation (the reference wheel's operator boundary, local_correlation.py:22-35)
@@ -797,6 +794,9 @@ static inline unsigned grid1d(int64_t total, int block) {
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// ROMAB200_LC_TILE=0 keeps every pixel on the per-pixel kernel (A/B measurements)
+static inline bool lc_tile_enabled() { static const bool on = [] { const char* e = getenv("ROMAB200_LC_TILE"); return !e || atoi(e) != 0; }(); return on; }
+
 extern "C" int romab200_refiner_prologue(const rb_refiner_prologue_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RB_REQUIRE(a->cf > 0 && a->cf <= 512, "refiner_prologue: cf=%d", a->cf);
@@ -813,7 +813,18 @@ extern "C" int romab200_refiner_prologue(const rb_refiner_prologue_args* a, void
     p.disp_scale = a->disp_scale; p.gx = a->grid_x; p.gy = a->grid_y; p.winx = a->win_x; p.winy = a->win_y;
     const int es = a->dtype == RB_F32 ? 4 : 2;
     p.vec_ok = (a->ldf * es) % 16 == 0 && (a->ldd * es) % 16 == 0 && ((uintptr_t)a->feat) % 16 == 0 && ((uintptr_t)a->d) % 16 == 0;
+    p.tile_done = nullptr;
+    p.corr_table = a->corr_table; p.ld_table = a->ld_corr_table;
+    RB_REQUIRE(!a->corr_table || (a->radius > 0 && a->ld_corr_table >= (int64_t)a->h * a->w), "refiner_prologue: corr_table needs a local correlation and ld >= h*w");
     int64_t pixels = (int64_t)a->D * a->h * a->w;
+    if (a->radius > 0 && a->dtype == RB_F32 && a->tile_done && !a->corr_table && p.vec_ok && a->cf % 16 == 0 && lc_tile_enabled()) {
+        const int tqy = a->radius == 7 ? LcTile<7>::TQY : LcTile<3>::TQY, tqx = LcTile<3>::TQX;
+        const int64_t tiles = (int64_t)a->D * ((a->h + tqy - 1) / tqy) * ((a->w + tqx - 1) / tqx);
+        RB_REQUIRE(a->radius == 2 || a->radius == 3 || a->radius == 7, "refiner_prologue: radius %d unsupported", a->radius);
+        RB_REQUIRE(a->tile_done_len >= tiles, "refiner_prologue: tile_done holds %d bytes, %lld tiles", a->tile_done_len, (long long)tiles);
+        if (int rc = refiner_prologue_tile(p, a->radius, (unsigned char*)a->tile_done, st)) return rc;
+        p.tile_done = (const unsigned char*)a->tile_done;
+    }
     if (a->radius == 0 && 2 * a->cf + a->emb <= 32 && a->ldd <= 32 && p.vec_ok) {
         unsigned g = (unsigned)((pixels + 255) / 256);      // thin stride-1 maps: one thread per pixel
         if (a->dtype == RB_F32) rb::launch_pdl(refiner_prologue_small_kernel<float>, dim3(g), dim3(256), 0, st, p);

@@ -24,6 +24,7 @@ together as a 3-channel fp32 state map [D, h, w, 3].
 from __future__ import annotations
 
 import math
+import os
 from contextlib import contextmanager
 from typing import Dict, Optional, Tuple
 
@@ -65,6 +66,7 @@ class Engine:
         self.overlap_cnn = True                  # VGG/proj branch on a side stream, overlapping ViT / GP / decoder
         self.gp_tensor_core = True               # all-pairs CosKernel on tcgen05 (split-fp16 operands) in the 16-bit modes
         self.fused_c144 = True                   # stride-2 refiner blocks as one fused DW + tcgen05-PW kernel
+        self.lc_table16 = os.environ.get("ROMAB200_LC_TABLE16", "1") != "0"   # parity mode: stride-16 local correlation gathered from an all-pairs tensor-core table
         self.fused_small_f32 = True              # fp32 modes: stride-1 (C = 24) refiner blocks as one fused fp32 CUDA-core kernel
         self._side = None
         self.profile: Optional[dict] = None      # set to {} to collect CUDA-event timings per stage (bench.py)
@@ -371,6 +373,17 @@ class Engine:
             with self.stage("  gp.split"):
                 call("romab200_split_f16x3", "rb_split_args", x=p16, dst=xa, rows=E * n, cols=cf, ldx=cf, ldd=3 * cf, row_norm=norms, layout_b=0)
                 call("romab200_split_f16x3", "rb_split_args", x=p16, dst=xb, rows=E * n, cols=cf, ldx=cf, ldd=3 * cf, row_norm=norms, layout_b=1)
+        self._corr16 = None
+        if self.split and self.lc_table16:
+            # the stride-16 refiner's local correlation (r = 7: 256 dot products of 512 channels per pixel) from ONE all-pairs
+            # contraction per direction on tcgen05: table[i, p, q] = <x_i[p], y_i[q]> / sqrt(512), gathered by the prologue
+            with self.stage("  gp.corr16"):
+                ps = self.split_pair(p16, E * n, cf, cf, name="gp.p16s")
+                tab = self.buf("ref.corr16", (D, n, ldw), dtype=torch.float32)
+                for i0, cnt, y0 in ([(0, b, b)] if D == b else [(0, b, b), (b, b, 0)]):
+                    self.gemm(ps.at(i0 * n * cf), ps.at(y0 * n * cf), tab.data_ptr() + i0 * n * ldw * 4, n, n, cf, cf, cf, ldw, dtype_c=f32,
+                              batch0=cnt, sa0=n * cf, sb0=n * cf, sc0=n * ldw, alpha=float(torch.rsqrt(torch.tensor(float(cf)))))
+                self._corr16 = (tab, ldw)
         with self.stage("  gp.kyy"):
             if gp_split:
                 self.gp_kernel_matrix_split(xs, xs, norms, norms, Wk, n, cf, ldw, batch=E, sa=n * cf, sb=n * cf, sc=stride_w,
@@ -479,8 +492,14 @@ class Engine:
         d = self.buf(f"ref.d.{tag}", (D * h * w, cp), zero=True)
         t = None if self.split else self.buf(f"ref.t.{tag}", (D * h * w, cp), zero=True)
         r = spec.radius
+        tiles = None
+        table, ld_table = (self._corr16 if s == 16 and getattr(self, "_corr16", None) else (None, 0))
+        if r and self.dt == cabi.RB_F32 and table is None:
+            # workspace of the tile-cooperative pass (coherent flow: one CTA per 8x2 / 8x4 pixels stages the union of their windows)
+            tiles = self.buf(f"ref.tiles.{tag}", (D * cabi.prologue_tiles(r, h, w),), dtype=torch.uint8, zero=True)
         with self.stage(f"  prologue{s}.{tag[:2]}"):
           call("romab200_refiner_prologue", "rb_refiner_prologue_args", feat=feat, ldf=ldf, n_img=E, y_shift=b,
+             tile_done=tiles, tile_done_len=tiles.numel() if tiles is not None else 0, corr_table=table, ld_corr_table=ld_table,
              state=state, d=d, ldd=cp, D=D, h=h, w=w, cf=spec.feat, emb=spec.emb, radius=r, dtype=self.dt,
              emb_weight=R["emb_w"], emb_bias=R["emb_b"],
              disp_scale=float(torch.tensor(40 / 32 * scale_factor, dtype=torch.float32)),

@@ -318,6 +318,112 @@ def test_refiner_prologue_blocks_tail(weights, s):
     close(state, exp_state, 1e-6)
 
 
+@pytest.mark.parametrize("s,h,w,kind", [(16, 12, 10, "smooth"), (16, 9, 14, "shift"), (8, 20, 27, "smooth"), (8, 17, 24, "shift"), (8, 16, 16, "mixed"),
+                                        (4, 23, 30, "smooth"), (4, 16, 24, "mixed"), (4, 40, 33, "random")])
+def test_refiner_prologue_tile_pass(weights, s, h, w, kind):
+    """refiner_prologue_tile_kernel<R> (one CTA per tile of pixels, the union of their windows staged in shared memory) against the
+    oracle's refiner input and against the per-pixel kernel, on coherent flow (identity + sub-pixel noise; shifted so that windows
+    leave the image), on flow that is coherent in one half only (the other half falls back to the per-pixel kernel) and on random flow."""
+    from oracle.roma_oracle import RomaOracle
+    from roma_b200 import arch
+    from roma_b200.packing import pad8
+    spec = arch.REFINERS[s]
+    E = D = 2
+    orc = RomaOracle(weights[0], weights[1])
+    g = torch.Generator().manual_seed(100 * s + h)
+    feat = rnd(E, spec.feat, h, w, seed=s + 7)
+    ys, xs = torch.linspace(-1 + 1 / h, 1 - 1 / h, h), torch.linspace(-1 + 1 / w, 1 - 1 / w, w)
+    gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+    ident = torch.stack((gx, gy))[None].expand(D, 2, h, w)
+    noise = torch.randn(D, 2, h, w, generator=g) * torch.tensor([1.0 / w, 1.0 / h]).view(1, 2, 1, 1)          # 0.5 pixel
+    if kind == "smooth":
+        flow = ident + noise
+    elif kind == "shift":                                  # windows of the border tiles leave the image on two sides
+        flow = ident * 1.05 + noise + torch.tensor([0.35, -0.4]).view(1, 2, 1, 1)
+    elif kind == "mixed":
+        flow = ident + noise
+        rnd_flow = torch.rand(D, 2, h, w, generator=g) * 2.2 - 1.1
+        flow[:, :, :, w // 2:] = rnd_flow[:, :, :, w // 2:]
+    else:
+        flow = torch.rand(D, 2, h, w, generator=g) * 2.2 - 1.1
+    cert = torch.zeros(D, 1, h, w)
+    fc = feat.cpu()
+    sf = 1.3
+    d_ref = orc.refiner_input(s, fc, torch.cat((fc[1:], fc[:1])), flow, sf)
+    R = _packed(weights).refiner[s]
+    cp, c = R["cp"], R["c"]
+    ldf = pad8(spec.feat)
+    featc = torch.zeros(E, h, w, ldf, device=DEV)
+    featc[..., :spec.feat] = feat.permute(0, 2, 3, 1)
+    state = torch.cat((flow, cert), 1).permute(0, 2, 3, 1).contiguous().to(DEV)
+    r = spec.radius
+    ntiles = D * cabi.prologue_tiles(r, h, w)
+    wx, wy = _windows(r, h, w)
+    outs = []
+    for tiles in (torch.full((ntiles,), 7, dtype=torch.uint8, device=DEV), None):
+        d = torch.zeros(D * h * w, cp, device=DEV)
+        call("romab200_refiner_prologue", "rb_refiner_prologue_args", feat=featc, ldf=ldf, n_img=E, y_shift=1, state=state, d=d, ldd=cp,
+             D=D, h=h, w=w, cf=spec.feat, emb=spec.emb, radius=r, dtype=F32, emb_weight=R["emb_w"], emb_bias=R["emb_b"],
+             disp_scale=float(torch.tensor(40 / 32 * sf, dtype=torch.float32)), grid_x=xs.to(DEV), grid_y=ys.to(DEV), win_x=wx, win_y=wy,
+             tile_done=tiles, tile_done_len=ntiles if tiles is not None else 0)
+        outs.append(d)
+        if tiles is not None:
+            done = tiles.cpu()
+            assert ((done == 0) | (done == 1)).all()                   # every tile reports
+            frac = done.float().mean().item()
+            if kind in ("smooth", "shift"):
+                assert frac == 1.0, frac
+            elif kind == "mixed":
+                assert 0.0 < frac < 1.0, frac
+            else:
+                assert frac < 0.5, frac
+    close(outs[0].view(D, h, w, cp)[..., :c].permute(0, 3, 1, 2), d_ref, 5e-5)
+    close(outs[0], outs[1], 2e-5)
+    assert (outs[0][:, c:] == 0).all()                                  # the zero padding of the rows is left alone
+
+
+@pytest.mark.parametrize("h,w", [(12, 10), (7, 9)])
+def test_refiner_prologue_corr_table(weights, h, w):
+    """Stride-16 prologue with the window dot products gathered from an all-pairs table (rb_refiner_prologue_args.corr_table) built by
+    romab200_gemm from split-fp16 pairs, against the oracle's refiner input."""
+    from oracle.roma_oracle import RomaOracle
+    from roma_b200 import arch
+    from roma_b200.packing import pad8
+    s = 16
+    spec = arch.REFINERS[s]
+    E = D = 2
+    n = h * w
+    orc = RomaOracle(weights[0], weights[1])
+    feat = rnd(E, spec.feat, h, w, seed=3)
+    flow = (torch.rand(D, 2, h, w, generator=torch.Generator().manual_seed(5)) * 2.2 - 1.1)
+    fc = feat.cpu()
+    sf = 1.0
+    d_ref = orc.refiner_input(s, fc, torch.cat((fc[1:], fc[:1])), flow, sf)
+    R = _packed(weights).refiner[s]
+    cp, c = R["cp"], R["c"]
+    cf = spec.feat
+    featc = feat.permute(0, 2, 3, 1).contiguous().to(DEV)                       # [E, h, w, 512]
+    hi = torch.empty(E * n, cf, dtype=torch.float16, device=DEV)
+    lo = torch.empty(E * n, cf, dtype=torch.float16, device=DEV)
+    call("romab200_split_f16s", "rb_split_pair_args", x=featc, hi=hi, lo=lo, rows=E * n, cols=cf, ldx=cf, ldd=cf)
+    ldt = pad8(n)
+    table = torch.zeros(D, n, ldt, device=DEV)
+    for i0, y0 in ((0, 1), (1, 0)):
+        call("romab200_gemm", "rb_gemm_args", A=hi[i0 * n:], A_lo=lo[i0 * n:], B=hi[y0 * n:], B_lo=lo[y0 * n:], C=table[i0], M=n, N=n, K=cf, lda=cf, ldb=cf,
+             ldc=ldt, dtype_ab=cabi.RB_F16S, dtype_c=F32, batch0=1, batch1=1, ntaps=1, alpha=float(torch.rsqrt(torch.tensor(float(cf)))))
+    ref_tab = torch.einsum("bpc,bqc->bpq", featc.view(E, n, cf).double(), featc.view(E, n, cf).double()[[1, 0]]) / math.sqrt(cf)
+    close(table[:, :, :n], ref_tab.float(), 2e-5)
+    state = torch.cat((flow, torch.zeros(D, 1, h, w)), 1).permute(0, 2, 3, 1).contiguous().to(DEV)
+    xs, ys = torch.linspace(-1 + 1 / w, 1 - 1 / w, w), torch.linspace(-1 + 1 / h, 1 - 1 / h, h)
+    wx, wy = _windows(spec.radius, h, w)
+    d = torch.zeros(D * n, cp, device=DEV)
+    call("romab200_refiner_prologue", "rb_refiner_prologue_args", feat=featc, ldf=cf, n_img=E, y_shift=1, state=state, d=d, ldd=cp,
+         D=D, h=h, w=w, cf=cf, emb=spec.emb, radius=spec.radius, dtype=F32, emb_weight=R["emb_w"], emb_bias=R["emb_b"],
+         disp_scale=float(torch.tensor(40 / 32 * sf, dtype=torch.float32)), grid_x=xs.to(DEV), grid_y=ys.to(DEV), win_x=wx, win_y=wy,
+         corr_table=table, ld_corr_table=ldt)
+    close(d.view(D, h, w, cp)[..., :c].permute(0, 3, 1, 2), d_ref, 5e-5)
+
+
 _PACKED = {}
 
 
