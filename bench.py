@@ -111,14 +111,19 @@ def cpu_reference_time(steps, warmup, budget_s=240.0, with_sample=True):
     return times, torch.get_num_threads()
 
 
-def local_corr_flow_sweep(dev, precision, tile_pass=True):
-    """The local-correlation prologue kernels alone, on smooth flow (identity + 0.5 pixel of noise: neighbouring pixels share their
+def local_corr_flow_sweep(dev, precision, mode="engine"):
+    """The local-correlation prologue launches alone, on smooth flow (identity + 0.5 pixel of noise: neighbouring pixels share their
     windows) and on random flow (uniform over the image: no sharing, what the seeded synthetic weights produce): ms per launch and the
-    compulsory HBM bytes of SURVEY 8d (read f0 + f1 + flow, write the window) per second, for the five launches of one direction pair."""
+    compulsory HBM bytes of SURVEY 8d (read f0 + f1 + flow, write the window) per second, for the five launches of one direction pair.
+    mode "engine" = what the parity mode runs (stride 16: split + two all-pairs tcgen05 GEMMs + the gathering prologue, replayed from a
+    CUDA graph; stride 4: tile-cooperative pass + per-pixel kernel for the tiles it declines; stride 8: per-pixel kernel);
+    "per_pixel" = the per-pixel kernel everywhere; "tile_all" = the tile-cooperative pass at every scale."""
     import torch
     from roma_b200 import arch, cabi
     from roma_b200.cabi import call
     dt = torch.float32 if precision.startswith("fp32") else (torch.float16 if precision == "fp16" else torch.bfloat16)
+    if dt != torch.float32:
+        mode = "per_pixel"
     code = cabi.DTYPE_CODE[dt]
     es = 4 if dt == torch.float32 else 2
     g = torch.Generator(device="cpu").manual_seed(0)
@@ -131,6 +136,7 @@ def local_corr_flow_sweep(dev, precision, tile_pass=True):
                 spec = arch.REFINERS[sc]
                 h = w = res // sc if sc != 16 else res // 14
                 D = E = 2
+                n = h * w
                 ldf = (spec.feat + 7) // 8 * 8
                 cp = (spec.channels + 7) // 8 * 8
                 feat = torch.randn(E, h, w, ldf, generator=g).to(dev, dt)
@@ -146,24 +152,100 @@ def local_corr_flow_sweep(dev, precision, tile_pass=True):
                 R = dict(emb_w=torch.randn(spec.emb, 2).to(dev), emb_b=torch.randn(spec.emb).to(dev))
                 kw = dict(feat=feat, ldf=ldf, n_img=E, y_shift=1, state=state, d=d, ldd=cp, D=D, h=h, w=w, cf=spec.feat, emb=spec.emb, radius=r, dtype=code,
                           emb_weight=R["emb_w"], emb_bias=R["emb_b"], disp_scale=1.25, grid_x=xs.to(dev), grid_y=ys.to(dev), win_x=wx, win_y=wy)
-                if dt == torch.float32 and tile_pass:       # workspace of the tile-cooperative pass (what the engine passes in the parity mode)
+                how = "per-pixel kernel"
+                pre = []                                   # launches before the prologue (table path)
+                if mode == "tile_all" or (mode == "engine" and r == 2):
                     tiles = torch.zeros(D * cabi.prologue_tiles(r, h, w), dtype=torch.uint8, device=dev)
                     kw.update(tile_done=tiles, tile_done_len=tiles.numel())
-                for _ in range(2):
+                    how = "tile-cooperative pass + per-pixel kernel for declined tiles"
+                elif mode == "engine" and sc == 16:
+                    cf = spec.feat
+                    hi, lo = torch.empty(E * n, cf, dtype=torch.float16, device=dev), torch.empty(E * n, cf, dtype=torch.float16, device=dev)
+                    ldt = (n + 7) // 8 * 8
+                    table = torch.zeros(D, n, ldt, device=dev)
+                    pre.append(lambda feat=feat, hi=hi, lo=lo, n=n, cf=cf: call("romab200_split_f16s", "rb_split_pair_args", x=feat, hi=hi, lo=lo, rows=E * n, cols=cf, ldx=cf, ldd=cf))
+                    for i0, y0 in ((0, 1), (1, 0)):
+                        pre.append(lambda i0=i0, y0=y0, hi=hi, lo=lo, table=table, n=n, cf=cf, ldt=ldt: call(
+                            "romab200_gemm", "rb_gemm_args", A=hi[i0 * n:], A_lo=lo[i0 * n:], B=hi[y0 * n:], B_lo=lo[y0 * n:], C=table[i0], M=n, N=n, K=cf, lda=cf,
+                            ldb=cf, ldc=ldt, dtype_ab=cabi.RB_F16S, dtype_c=cabi.RB_F32, batch0=1, batch1=1, ntaps=1, alpha=float(cf) ** -0.5))
+                    kw.update(corr_table=table, ld_corr_table=ldt)
+                    how = "split + 2 all-pairs tcgen05 GEMMs + gathering prologue (CUDA graph of the 4 launches)"
+
+                def launches():
+                    for f in pre:
+                        f()
                     call("romab200_refiner_prologue", "rb_refiner_prologue_args", **kw)
+                side = torch.cuda.Stream()
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        launches()
+                torch.cuda.synchronize()
+                run = launches
+                if pre:                                    # several short launches: replay them from a graph so that host launch latency is not timed
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        launches()
+                    run = graph.replay
                 ts = []
                 for _ in range(5):
                     flush.zero_()
                     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    s.record(); call("romab200_refiner_prologue", "rb_refiner_prologue_args", **kw); e.record()
+                    s.record(); run(); e.record()
                     torch.cuda.synchronize()
                     ts.append(s.elapsed_time(e))
                 ms = sorted(ts)[2]
                 nbytes = D * h * w * ((2 * spec.feat + spec.k) * es + 8)        # f0 + f1 read once, window written once, flow read
-                per[f"stride{sc}@{res}"] = {"ms": round(ms, 4), "gbs": round(nbytes / ms / 1e6, 1)}
+                per[f"stride{sc}@{res}"] = {"ms": round(ms, 4), "gbs": round(nbytes / ms / 1e6, 1), "how": how}
                 tot_ms += ms; tot_bytes += nbytes
         out[kind] = {"ms_per_pair": round(tot_ms, 4), "hbm_gbs": round(tot_bytes / tot_ms / 1e6, 1), "launches": per}
     return out
+
+
+def allpairs_kernel_leg(dev, reps=20):
+    """The all-pairs CosKernel launches of one pair exactly as the engine issues them (K_AA | K_BB batched into the Cholesky workspace,
+    K_AB and K_BA as split pairs for mu = K_xy alpha; 1600 x 1600 x 512 each, split-fp16 operands on tcgen05), `reps` times in ONE CUDA
+    graph so that host launch latency (3 launches of ~30 us each) is not in the timed region; inputs are L2-resident as in the step
+    (the split kernel that produces them runs right before)."""
+    import torch
+    from roma_b200 import arch, cabi
+    from roma_b200.cabi import call
+    n, cf, E = (COARSE // 14) ** 2, arch.PROJ[16][1], 2
+    ldw = (n + 7) // 8 * 8
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(E * n, cf, generator=g).to(dev)
+    norms = torch.empty(E * n, device=dev)
+    call("romab200_row_norms", "rb_rownorm_args", x=x, out=norms, rows=E * n, cols=cf, ldx=cf, dtype=cabi.RB_F32)
+    hi, lo = torch.empty(E * n, cf, dtype=torch.float16, device=dev), torch.empty(E * n, cf, dtype=torch.float16, device=dev)
+    call("romab200_split_f16s", "rb_split_pair_args", x=x, hi=hi, lo=lo, rows=E * n, cols=cf, ldx=cf, ldd=cf, row_norm=norms)
+    stride_w = (n + arch.GP_DIM) * ldw
+    Wk = torch.zeros(E, n + arch.GP_DIM, ldw, device=dev)
+    kxy_hi, kxy_lo = torch.zeros(E, n, ldw, dtype=torch.float16, device=dev), torch.zeros(E, n, ldw, dtype=torch.float16, device=dev)
+    common = dict(M=n, N=n, K=cf, lda=cf, ldb=cf, ldc=ldw, dtype_ab=cabi.RB_F16S, ntaps=1, alpha=1.0, epi=cabi.EPI_COSKERNEL, sna0=n, snb0=n,
+                  eps=arch.GP_COS_EPS, inv_t=1.0 / arch.GP_TEMPERATURE, cos_normalized=1)
+
+    def three():
+        call("romab200_gemm", "rb_gemm_args", A=hi, A_lo=lo, B=hi, B_lo=lo, C=Wk, dtype_c=cabi.RB_F32, batch0=E, batch1=1, sa0=n * cf, sb0=n * cf, sc0=stride_w,
+             norm_a=norms, norm_b=norms, diag_add=arch.GP_SIGMA_NOISE, **common)
+        for i0, y0 in ((0, 1), (1, 0)):
+            call("romab200_gemm", "rb_gemm_args", A=hi[i0 * n:], A_lo=lo[i0 * n:], B=hi[y0 * n:], B_lo=lo[y0 * n:], C=kxy_hi[i0], C_lo=kxy_lo[i0], dtype_c=cabi.RB_F16S,
+                 batch0=1, batch1=1, sa0=n * cf, sb0=n * cf, sc0=n * ldw, norm_a=norms[i0 * n:], norm_b=norms[y0 * n:], diag_add=0.0, **common)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            three()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(reps):
+            three()
+    ts = []
+    for _ in range(7):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); graph.replay(); e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) / reps)
+    return {"ms_per_pair": sorted(ts)[3], "launches_per_pair": 3, "flops_per_pair_reference": 4 * 2.0 * n * n * cf, "flops_per_pair_computed": 4 * 2.0 * n * n * cf,
+            "reps_in_graph": reps}
 
 
 def preprocess_leg(dev, reps=5):
@@ -509,12 +591,16 @@ def run_ours(args):
             if os.path.exists(tpath):
                 traffic = json.load(open(tpath)).get(dom)
             passes = 3.0 if dom == "tcgen05-split" else 1.0
-            roofline = {"kernel": f"romab200_gemm[{dom}]", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"],
-                        "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
-                        "achieved_executed": ach * passes, "frac_executed": ach * passes / peaks["bf16_sustained"],
+            roofline = {"kernel": f"romab200_gemm[{dom}]", "bound": "tensor", "achieved": ach * passes, "peak": peaks["bf16_sustained"],
+                        "unit": "TFLOP/s", "frac": ach * passes / peaks["bf16_sustained"],
+                        "flops_definition": ("tensor-core FLOPs of the algorithm as it runs on the f16 pipe: an fp32-class product from split-fp16 operand pairs is THREE "
+                                             "f16 MMAs per k-step (hi.hi, hi.lo, lo.hi; 22 significand bits), i.e. 3 x 2MNK per launch - each term is needed, none is a "
+                                             "recomputation; ncu's sm__pipe_tensor_cycles_active of the same kernel (profiles/r02_ncu_gemm_fc1_qkv_tcgen05_split_final.txt: "
+                                             "46-53 %) is the independent check" if passes > 1 else "2MNK per launch"),
+                        "fp32_equivalent": {"achieved": ach, "frac": ach / peaks["bf16_sustained"],
+                                            "note": "2MNK per launch (the FLOPs of the fp32 contraction the reference performs) against the same bf16 peak: "
+                                                    "bounded by 1/3 in the split mode"} if passes > 1 else None,
                         "passes": passes,
-                        "passes_note": "algorithmic FLOPs = the fp32 contraction 2MNK; the split-fp16 parity mode executes three f16 MMAs per "
-                                       "algorithmic MMA (hi.hi, hi.lo, lo.hi), so its ceiling on this axis is 1/3" if passes > 1 else None,
                         "traffic": traffic["dram_bytes"] if traffic else None,
                         "traffic_launch": traffic["launch"] if traffic else None,
                         "peak_source": peaks["source"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
@@ -535,10 +621,25 @@ def run_ours(args):
             executed = 3.0 if cos_backend == "tcgen05-split" else 1.0
             ach = cos_flops / split / (cos_ms / 1e3) / 1e12
             pk = peaks["bf16_sustained"] if cos_backend.startswith("tcgen05") else 72.0
-            extra.append({"kernel": f"all-pairs CosKernel (romab200_gemm, RB_EPI_COSKERNEL, {cos_backend})", "bound": "tensor" if cos_backend.startswith("tcgen05") else "fp32",
-                          "achieved": ach, "achieved_executed": cos_flops * executed / (cos_ms / 1e3) / 1e12, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
-                          "launches_per_step": cos_n / args.steps, "ms_per_step": cos_ms / args.steps,
-                          "note": "four 1600x1600x512 problems per pair (2.6 GFLOP each, 1.5 us at peak): size-limited, see DESIGN.md"})
+            entry = {"kernel": f"all-pairs CosKernel (romab200_gemm, RB_EPI_COSKERNEL, {cos_backend})", "bound": "tensor" if cos_backend.startswith("tcgen05") else "fp32",
+                     "achieved": ach, "achieved_executed": cos_flops * executed / (cos_ms / 1e3) / 1e12, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
+                     "launches_per_step": cos_n / args.steps, "ms_per_step": cos_ms / args.steps,
+                     "measured_in": "eager launches of the step, CUDA events around each launch (includes the host's launch latency: ~100 us for a ~30 us kernel)",
+                     "note": "four 1600x1600x512 problems per pair (2.6 GFLOP each, 1.5 us at peak): size-limited, see DESIGN.md"}
+            if cos_backend == "tcgen05-split" and world == 1:
+                try:
+                    leg = allpairs_kernel_leg(dev)
+                    ach = leg["flops_per_pair_reference"] / (leg["ms_per_pair"] / 1e3) / 1e12
+                    entry.update({"eager": {k: entry[k] for k in ("achieved", "achieved_executed", "frac", "ms_per_step", "measured_in")},
+                                  "achieved": 3.0 * ach, "frac": 3.0 * ach / pk, "achieved_executed": 3.0 * ach,
+                                  "fp32_equivalent": {"achieved": ach, "frac": ach / pk, "note": "2MNK of the four matrices the reference computes per pair"},
+                                  "flops_definition": "3 x 2MNK per matrix: split-fp16 operand pairs, three f16 MMAs per k-step (see roofline.flops_definition)",
+                                  "ms_per_step": leg["ms_per_pair"] * P,
+                                  "measured_in": f"the engine's 3 launches per pair, {leg['reps_in_graph']} pairs replayed from one CUDA graph (device time only, "
+                                                 "operands L2-resident as in the step)"})
+                except Exception as exc:
+                    entry["graph_leg_error"] = f"{type(exc).__name__}: {exc}"[:200]
+            extra.append(entry)
         lc_fma, lc_bytes = 0.0, 0.0
         try:
             lc_sweep = local_corr_flow_sweep(dev, args.precision)
@@ -552,16 +653,26 @@ def run_ours(args):
                     px = 2 * P * (res // sc) ** 2
                     lc_fma += px * (2 * spec.radius + 2) ** 2 * spec.feat
                     lc_bytes += px * (2 * spec.feat + spec.k) * esz          # f0 + f1 read once, window written once
-        lc_ms = sum(v for k, v in stages.items() if k.strip().startswith("prologue") and arch.REFINERS[int(k.strip()[8:].split(".")[0])].radius)
+        lc_ms = sum(v for k, v in stages.items() if (k.strip().startswith("prologue") and arch.REFINERS[int(k.strip()[8:].split(".")[0])].radius) or k.strip() == "gp.corr16")
+        lc_pp = None
+        if world == 1 and args.precision == "fp32":
+            try:
+                lc_pp = {m: {k: {"ms_per_pair": v["ms_per_pair"], "hbm_gbs": v["hbm_gbs"], "ms": {a: b["ms"] for a, b in v["launches"].items()}}
+                             for k, v in local_corr_flow_sweep(dev, args.precision, m).items()} for m in ("per_pixel", "tile_all")}
+            except Exception as exc:
+                lc_pp = {"error": f"{type(exc).__name__}: {exc}"[:200]}
         if lc_ms > 0:
-            extra.append({"kernel": "local correlation (refiner_prologue_kernel<R=7,3,2>: window dot products + feature gather)", "bound": "fp32",
-                          "achieved": 2 * lc_fma / (lc_ms / 1e3) / 1e12, "peak": 72.0, "unit": "TFLOP/s", "frac": 2 * lc_fma / (lc_ms / 1e3) / 1e12 / 72.0,
-                          "peak_source": "nominal: 148 SMs x 128 fp32 FMA/clk x 1.9 GHz (no measured fp32 figure in MEASURED_PEAKS.json)",
-                          "hbm_achieved_gbs": lc_bytes / (lc_ms / 1e3) / 1e9, "hbm_frac": lc_bytes / (lc_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
-                          "ms_per_step": lc_ms,
+            extra.append({"kernel": "local correlation (stride 16: all-pairs tcgen05 table + gather; stride 8: refiner_prologue_kernel<3>; stride 4: "
+                                    "refiner_prologue_tile_kernel<2> + refiner_prologue_kernel<2>) incl. the x / grid_sample / embedding part of the prologue",
+                          "bound": "hbm", "achieved": lc_bytes / (lc_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": lc_bytes / (lc_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                          "fp32_fma_tflops": 2 * lc_fma / (lc_ms / 1e3) / 1e12, "fp32_fma_frac_of_nominal_72": 2 * lc_fma / (lc_ms / 1e3) / 1e12 / 72.0,
+                          "ms_per_step": lc_ms, "measured_in": "eager launches of the step (the flow of the seeded synthetic weights is random: no window sharing)",
                           "flow_sweep": lc_sweep, "flow_sweep_hbm_frac": ({k: round(v["hbm_gbs"] / peaks["hbm_gbs"], 4) for k, v in lc_sweep.items()} if lc_sweep and "error" not in lc_sweep else None),
-                          "note": "the windows of neighbouring pixels overlap, so f1 is served from L1/L2 (ncu: 3-50 MB of DRAM reads per launch); "
-                                  "the limiter is CUDA-core instruction issue (8 FMA per 21 instructions), not HBM: see DESIGN.md"})
+                          "flow_sweep_other_kernels": lc_pp,
+                          "note": "algorithmic bytes = SURVEY 8d (f0 + f1 + flow read once, window written once).  The windows of neighbouring pixels overlap, so f1 "
+                                  "is served from L1/L2, not HBM; the CUDA-core kernels are bound by the 4 bytes of L1/shared-memory bandwidth each fp32 FMA "
+                                  "needs (floor 0.29 ms per pair = 0.24 of the HBM roofline, DESIGN.md 4); only stride 16, where the table is small, goes "
+                                  "through the tensor cores"})
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             times, threads = cpu_reference_time(1, 1, with_sample=not args.no_sample)

@@ -293,7 +293,10 @@ int romab200_match_epilogue(const rb_match_epilogue_args* args, void* stream);
 
 /* sample(): Gaussian KDE density (kde.py:4-12) without materialising the NxN matrix.
  * x [n,4] fp32; density[i] = sum_j exp(-||h(x_i)-h(x_j)||^2 / (2 std^2)), h = fp16 rounding when half != 0 */
-typedef struct { const float* x; float* density; int32_t n; float std; int32_t half; } rb_kde_args;
+typedef struct { const float* x; float* density; int32_t n; float std; int32_t half;
+                 /* optional: workspace of splits * n floats; the j range is then cut into `splits` parts summed in a fixed order by a second
+                  * kernel (more CTAs than SMs for the 40000-point problem of sample()).  NULL / splits <= 1: one pass */
+                 float* workspace; int32_t splits; } rb_kde_args;
 int romab200_kde_density(const rb_kde_args* args, void* stream);
 
 /* sample(): weighted sampling WITHOUT replacement on the device (the two torch.multinomial draws of matcher.py:613-617, 626-628).

@@ -131,7 +131,7 @@ _FIELD_DTYPES = {
     "rb_refiner_tail_args": {"d": "dtype", "weight": _F32, "bias": _F32, "state": _F32, "delta_out": _F32},
     "rb_resize_args": {"in": _F32, "out": _F32},
     "rb_match_epilogue_args": {"state": _F32, "coarse_state": _F32, "warp": _F32, "cert": _F32, "grid_x": _F32, "grid_y": _F32},
-    "rb_kde_args": {"x": _F32, "density": _F32},
+    "rb_kde_args": {"x": _F32, "density": _F32, "workspace": _F32},
     "rb_preprocess_args": {"in": torch.uint8, "tmp": torch.uint8, "out_u8": torch.uint8, "out": _F32, "bounds_x": torch.int32, "kk_x": torch.int32,
                            "bounds_y": torch.int32, "kk_y": torch.int32},
     "rb_sample_args": {"values": _F32, "out_idx": torch.int32, "out_weights": _F32, "keys": _F32, "scratch": torch.int32, "seed_dev": torch.int64},

@@ -244,14 +244,43 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
         // ---- element-wise part in the row-per-lane layout (every branch is warp-uniform) ----
         if (e.epi == RB_EPI_COSKERNEL) {
             const float na = m < p.M ? e.norm_a[m] : 1.f;
+            if (e.cos_normalized) {
+                // operands are the L2-normalised rows: c = acc * pn / (pn + eps) = acc * (1 - eps / (pn + eps)).  eps / (pn + eps) is ~1e-9 of
+                // the result, so an approximate reciprocal (2 ulp) leaves the factor correctly rounded in all but exotic cases (pn < 1e-2);
+                // exp(x) = 2^(x log2 e) with x in [-2/T, 0]: the input rounding costs |x log2 e| 2^-24 < 1e-6 relative, an order below the
+                // error of the split contraction itself (8e-6 vs float64).  15 instead of 30 instructions per element: this epilogue, not
+                // the 8-k-block main loop, bounds the launch (ncu: tensor pipe 18 % active).
+                const float k2 = e.inv_t * 1.4426950408889634f;
     #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = nb + j;
-                const float pn = na * s_vec0[cb + j];
-                const float sc = e.cos_normalized ? pn / (pn + e.eps) : 1.0f / (pn + e.eps);
-                float r = expf((v[j] * sc - 1.0f) * e.inv_t);
-                if (m == n) r += e.diag_add;
-                v[j] = r;
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(&s_vec0[cb + 4 * j]);
+                    const float bn[4] = {b4.x, b4.y, b4.z, b4.w};
+    #pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float pe = fmaf(na, bn[t], e.eps);
+                        float rc;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(pe));
+                        const float sc = fmaf(-e.eps, rc, 1.0f);
+                        const float x2 = fmaf(v[4 * j + t], sc, -1.0f) * k2;
+                        float r;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x2));
+                        v[4 * j + t] = r;
+                    }
+                }
+                if (e.diag_add != 0.f && m >= nb && m < nb + 32) {     // the diagonal crosses this 32-column chunk in at most one lane per column
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j) if (m == nb + j) v[j] += e.diag_add;
+                }
+            } else {
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = nb + j;
+                    const float pn = na * s_vec0[cb + j];
+                    const float sc = 1.0f / (pn + e.eps);
+                    float r = expf((v[j] * sc - 1.0f) * e.inv_t);
+                    if (m == n) r += e.diag_add;
+                    v[j] = r;
+                }
             }
         } else {
             if (e.alpha != 1.0f) {

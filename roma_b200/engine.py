@@ -67,6 +67,8 @@ class Engine:
         self.gp_tensor_core = True               # all-pairs CosKernel on tcgen05 (split-fp16 operands) in the 16-bit modes
         self.fused_c144 = True                   # stride-2 refiner blocks as one fused DW + tcgen05-PW kernel
         self.lc_table16 = os.environ.get("ROMAB200_LC_TABLE16", "1") != "0"   # parity mode: stride-16 local correlation gathered from an all-pairs tensor-core table
+        self.lc_tile_radii = (2,)                # fp32 maps: window radii whose prologue also runs the tile-cooperative pass (measured: wins on coherent
+                                                 # flow at r = 2, ties with the per-pixel kernel's L1 hits at r = 3; r = 7 uses the table above)
         self.fused_small_f32 = True              # fp32 modes: stride-1 (C = 24) refiner blocks as one fused fp32 CUDA-core kernel
         self._side = None
         self.profile: Optional[dict] = None      # set to {} to collect CUDA-event timings per stage (bench.py)
@@ -494,7 +496,7 @@ class Engine:
         r = spec.radius
         tiles = None
         table, ld_table = (self._corr16 if s == 16 and getattr(self, "_corr16", None) else (None, 0))
-        if r and self.dt == cabi.RB_F32 and table is None:
+        if r in self.lc_tile_radii and self.dt == cabi.RB_F32 and table is None:
             # workspace of the tile-cooperative pass (coherent flow: one CTA per 8x2 / 8x4 pixels stages the union of their windows)
             tiles = self.buf(f"ref.tiles.{tag}", (D * cabi.prologue_tiles(r, h, w),), dtype=torch.uint8, zero=True)
         with self.stage(f"  prologue{s}.{tag[:2]}"):
@@ -662,6 +664,9 @@ class Engine:
 
     def kde(self, x: torch.Tensor, std: float = 0.1, half: bool = True):
         x = x.contiguous().float()
-        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
-        call("romab200_kde_density", "rb_kde_args", x=x, density=out, n=x.shape[0], std=std, half=int(half))
+        n = x.shape[0]
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+        splits = 16 if n >= 8192 else 1
+        ws = torch.empty(splits * n, dtype=torch.float32, device=x.device) if splits > 1 else None
+        call("romab200_kde_density", "rb_kde_args", x=x, density=out, n=n, std=std, half=int(half), workspace=ws, splits=splits)
         return out

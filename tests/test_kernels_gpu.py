@@ -507,6 +507,16 @@ def test_kde_density():
     call("romab200_kde_density", "rb_kde_args", x=x.to(DEV), density=out32, n=n, std=0.1, half=0)
     ref32 = (-torch.cdist(x.double(), x.double()) ** 2 / (2 * 0.1 ** 2)).exp().sum(-1)
     close(out32, ref32.float(), 2e-3)
+    # j range cut into splits summed in a fixed order (what sample() uses for its 40000 points): same densities up to the fp32 summation order
+    for splits in (2, 5, 64):
+        ws = torch.zeros(splits * n, device=DEV)
+        outs = torch.zeros(n, device=DEV)
+        call("romab200_kde_density", "rb_kde_args", x=x.to(DEV), density=outs, n=n, std=0.1, half=1, workspace=ws, splits=splits)
+        ulp = (out.abs() * 2.0 ** -10).clamp_min(2.0 ** -14)               # one fp16 ulp of the rounded density
+        assert ((outs - out).abs() <= ulp).all() and ((outs - out).abs() > 0).float().mean().item() < 0.02
+        outs32 = torch.zeros(n, device=DEV)
+        call("romab200_kde_density", "rb_kde_args", x=x.to(DEV), density=outs32, n=n, std=0.1, half=0, workspace=ws, splits=splits)
+        close(outs32, out32, 1e-4)
 
 
 @pytest.mark.parametrize("mode", ["bilinear", "nearest"])
