@@ -90,6 +90,9 @@ typedef struct {
     /* second planes of RB_F16S operands / output (dtype_ab == RB_F16S: A_lo and B_lo, same geometry as A and B;
        dtype_c == RB_F16S: C_lo, same pitch as C); NULL otherwise */
     const void* A_lo; const void* B_lo; void* C_lo;
+    /* tcgen05 back-end: upper bound on the persistent grid (0 = one CTA per SM).  A GEMM running on a side stream beside a chain of short
+       dependent kernels (the GP solve) leaves the remaining SMs free, so that those kernels start without waiting for a whole GEMM. */
+    int32_t max_ctas;
 } rb_gemm_args;
 int romab200_gemm(const rb_gemm_args* args, void* stream);
 

@@ -927,6 +927,8 @@ static int sm_count() {
     return n[dev];
 }
 
+static thread_local int g_max_ctas = 0;       // rb_gemm_args.max_ctas of the call being launched (0: no cap)
+
 template <int BN, bool SPLIT>
 static int launch_tc(const TcMaps& maps, TcParams& p, int zdim, cudaStream_t st) {
     using Cfg = TcCfg<BN, SPLIT>;
@@ -943,7 +945,8 @@ static int launch_tc(const TcMaps& maps, TcParams& p, int zdim, cudaStream_t st)
     const long long total = (long long)p.tiles_m * p.tiles_n * zdim;
     RB_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
     p.total_tiles = (int)total;
-    const int resident = sm_count() * Cfg::CTAS_PER_SM;
+    int resident = sm_count() * Cfg::CTAS_PER_SM;
+    if (g_max_ctas > 0 && g_max_ctas < resident) resident = g_max_ctas;
     const int grid = p.total_tiles < resident ? p.total_tiles : resident;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
@@ -975,7 +978,8 @@ static int launch_tc_pair(const TcMaps& maps, TcParams& p, int zdim, cudaStream_
     const long long total = (long long)p.tiles_m * p.tiles_n * zdim;
     RB_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
     p.total_tiles = (int)total;
-    const int pairs = sm_count() / 2;
+    int pairs = sm_count() / 2;
+    if (g_max_ctas > 1 && g_max_ctas / 2 < pairs) pairs = g_max_ctas / 2;
     const int nclusters = p.total_tiles < pairs ? p.total_tiles : pairs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * nclusters); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
@@ -1007,6 +1011,7 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
     RB_REQUIRE(!split || (a->A_lo && a->B_lo), "gemm_tc: split-fp16 operands need A_lo and B_lo");
     RB_REQUIRE(a->dtype_c != RB_F16S || a->C_lo, "gemm_tc: split-fp16 output needs C_lo");
     TcParams p;
+    g_max_ctas = a->max_ctas;
     p.M = a->M; p.N = a->N; p.K = a->K;
     p.batch1 = a->batch1 > 0 ? a->batch1 : 1;
     const int batch0 = a->batch0 > 0 ? a->batch0 : 1;

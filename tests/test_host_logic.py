@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     assert len(cabi.FUNCTIONS) >= 20
     for fn in cabi.FUNCTIONS:
         assert hasattr(lib, fn), fn
-    assert ctypes.sizeof(cabi.STRUCTS["rb_gemm_args"]) == 360
+    assert ctypes.sizeof(cabi.STRUCTS["rb_gemm_args"]) == 368
 
 
 def test_fold_bn_matches_batchnorm(weights):
@@ -119,7 +119,7 @@ def test_engine_dry_run(weights, monkeypatch, symmetric, upsample, split):
     eng.w = PackedWeights(weights[0], weights[1], eng.device, torch.float32, split=split)
     eng._buf, eng._const, eng.debug, eng.profile, eng.gemm_profile, eng.use_flash_attn, eng.gp_algo = {}, {}, None, None, None, True, (3 if split else 2)
     eng.overlap_cnn, eng._side, eng.gp_tensor_core, eng.fused_c144, eng.fused_small_f32 = False, None, True, True, True
-    eng.lc_table16, eng.lc_tile_radii = True, (2,)
+    eng.lc_table16, eng.lc_tile_radii, eng.side_ctas = True, (2,), 0
     for t in _tensors(eng.w):
         rec.track(t)
     orig_buf, orig_const = eng.buf, eng.const
