@@ -1062,6 +1062,9 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
     if (!a->trans_b && pair_mode() && (BN == 256 || BN == 192)) {
         const long long pair_tiles = (long long)((a->M + 255) / 256) * ((a->N + BN - 1) / BN) * zdim;
         if (pair_mode() == 2 || pair_tiles >= 40) pair_bn = BN;
+        // split operands: a 256-wide tile's two accumulators fill TMEM, so its drain is exposed; 128-wide pair tiles double-buffer them
+        static const int split_pair_bn = [] { const char* e = getenv("ROMAB200_GEMM_SPLIT_PAIR_BN"); return e ? atoi(e) : 0; }();
+        if (pair_bn && split && split_pair_bn == 128 && a->N % 128 == 0) pair_bn = 128;
     }
     TcMaps maps;
     const uint64_t a_inner = p.ntaps > 1 ? p.k_per_tap : a->K;
@@ -1097,6 +1100,7 @@ int gemm_tc(const rb_gemm_args* a, cudaStream_t stream) {
             p.epi_mode = 0;
         }
     }
+    if (pair_bn == 128) return launch_tc_pair<128, true>(maps, p, zdim, stream);
     if (pair_bn == 256) return split ? launch_tc_pair<256, true>(maps, p, zdim, stream) : launch_tc_pair<256, false>(maps, p, zdim, stream);
     if (pair_bn == 192) return split ? launch_tc_pair<192, true>(maps, p, zdim, stream) : launch_tc_pair<192, false>(maps, p, zdim, stream);
     return split ? dispatch_tc<true>(BN, maps, p, zdim, stream) : dispatch_tc<false>(BN, maps, p, zdim, stream);
