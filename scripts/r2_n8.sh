@@ -1,6 +1,6 @@
 #!/bin/bash
 # 8-GPU box: BASELINE configs[2] (64 pairs over 8 GPUs) and configs[3] (roma_indoor, 32 pairs over 4 GPUs) with the NCCL scatter / gather in
-# the timed region, the default weak-scaling line at N = 8 / 4 / 2, and the NCCL sharding test
+# the timed region (the default weak-scaling lines at N = 1, 2, 4, 8 are the driver's SCALE run)
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
 run() { # name nproc port args...
@@ -10,18 +10,15 @@ run() { # name nproc port args...
 }
 run bench_cfg2_n8_g64 8 29521 --steps 4 --warmup 3 --global-pairs 64 --pairs-per-gpu 8
 run bench_cfg3_indoor_n4_g32 4 29522 --steps 4 --warmup 3 --global-pairs 32 --pairs-per-gpu 8 --model indoor
-run bench_default_n8 8 29523 --steps 10 --warmup 3
-run bench_default_n4 4 29524 --steps 10 --warmup 3
-run bench_default_n2 2 29525 --steps 10 --warmup 3
-timeout 600 python -m pytest tests/test_sharding_gpu.py -m gpu -q -p no:cacheprovider --timeout 500 > gpurun_out/pytest_sharding_n8box.log 2>&1; tail -n 3 gpurun_out/pytest_sharding_n8box.log
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -p no:cacheprovider --timeout 200 -k "prologue" > gpurun_out/pytest_prologue_n8box.log 2>&1; tail -n 2 gpurun_out/pytest_prologue_n8box.log
 python - <<'PY'
 import json
-for n in ("bench_cfg2_n8_g64", "bench_cfg3_indoor_n4_g32", "bench_default_n8", "bench_default_n4", "bench_default_n2"):
+for n in ("bench_cfg2_n8_g64", "bench_cfg3_indoor_n4_g32"):
     f = f"gpurun_out/{n}.json"
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(n, "value", round(d["value"], 2), "ms", round(d["ms_per_step"], 2), "e2e", round(d["e2e"]["value"], 2), "scaling", d["scaling"], "|", d["config"]["workload"],
               d["config"].get("nccl_bytes_per_step"), "parity", (d.get("parity") or {}).get("certainty"))
     except Exception as e:
-        print(f, "parse failed", e); print(open(f).read()[-400:])
+        print(f, "parse failed", e); print(open(f).read()[-400:]); print(open(f.replace(".json", ".err")).read()[-800:])
 PY
