@@ -203,29 +203,14 @@ __global__ void __launch_bounds__(128) refiner_prologue_kernel(const ProloguePar
     constexpr int S = 2 * R + 2;
     __shared__ float dtab_all[4][R > 0 ? S * S : 1];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t pix = (int64_t)blockIdx.x * 4 + wid;
     const int64_t hw = (int64_t)p.h * p.w;
-    // after a tile-cooperative pass (tile_done != nullptr) the grid is over ITS tiles: a CTA whose tile is finished leaves at once
-    // (one flag read per 16 / 32 pixels instead of one CTA per 4 pixels), otherwise its four warps walk the tile's pixels
-    constexpr int TQX = LcTile<R>::TQX, TQY = LcTile<R>::TQY;
-    const bool tile_mode = R > 0 && p.tile_done != nullptr;
-    if (tile_mode && p.tile_done[blockIdx.x]) return;                 // written by refiner_prologue_tile_kernel
-    const int iters = tile_mode ? TQX * TQY / 4 : 1;
-    for (int it = 0; it < iters; ++it) {
-    int64_t pix;
-    int item, rem, y, x;
-    if (tile_mode) {
-        const int tiles_x = (p.w + TQX - 1) / TQX, tiles_y = (p.h + TQY - 1) / TQY;
-        item = blockIdx.x / (tiles_x * tiles_y);
-        const int trem = blockIdx.x - item * tiles_x * tiles_y, q = it * 4 + wid;
-        y = (trem / tiles_x) * TQY + q / TQX; x = (trem % tiles_x) * TQX + q % TQX;
-        if (y >= p.h || x >= p.w) continue;
-        rem = y * p.w + x; pix = (int64_t)item * hw + rem;
-    } else {
-        pix = (int64_t)blockIdx.x * 4 + wid;
-        if (pix >= p.D * hw) return;
-        item = (int)(pix / hw);
-        rem = (int)(pix - item * hw);
-        y = rem / p.w; x = rem - y * p.w;
+    if (pix >= p.D * hw) return;
+    const int item = (int)(pix / hw);
+    const int rem = (int)(pix - item * hw);
+    const int y = rem / p.w, x = rem - y * p.w;
+    if constexpr (R > 0) {
+        if (p.tile_done && p.tile_done[lc_tile_index<R>(item, y, x, p.h, p.w)]) return;     // written by refiner_prologue_tile_kernel
     }
     const float fx = p.state[pix * 3 + 0], fy = p.state[pix * 3 + 1];
     const T* feat = (const T*)p.feat;
@@ -289,7 +274,6 @@ __global__ void __launch_bounds__(128) refiner_prologue_kernel(const ProloguePar
     if constexpr (R > 0)
         local_corr_warp<T, R, T>(xrow, yimg, p.ldf, fx, fy, p.h, p.w, cf, rsqrtf((float)cf), p.winx, p.winy, dtab_all[wid],
                                  drow + 2 * cf + p.emb, lane, p.corr_table ? p.corr_table + pix * p.ld_table : nullptr);
-    }
 }
 
 // stand-alone local correlation (the reference wheel's operator boundary, local_correlation.py:22-35)
@@ -830,7 +814,6 @@ extern "C" int romab200_refiner_prologue(const rb_refiner_prologue_args* a, void
     const int es = a->dtype == RB_F32 ? 4 : 2;
     p.vec_ok = (a->ldf * es) % 16 == 0 && (a->ldd * es) % 16 == 0 && ((uintptr_t)a->feat) % 16 == 0 && ((uintptr_t)a->d) % 16 == 0;
     p.tile_done = nullptr;
-    int64_t tile_count = 0;
     p.corr_table = a->corr_table; p.ld_table = a->ld_corr_table;
     RB_REQUIRE(!a->corr_table || (a->radius > 0 && a->ld_corr_table >= (int64_t)a->h * a->w), "refiner_prologue: corr_table needs a local correlation and ld >= h*w");
     int64_t pixels = (int64_t)a->D * a->h * a->w;
@@ -841,7 +824,6 @@ extern "C" int romab200_refiner_prologue(const rb_refiner_prologue_args* a, void
         RB_REQUIRE(a->tile_done_len >= tiles, "refiner_prologue: tile_done holds %d bytes, %lld tiles", a->tile_done_len, (long long)tiles);
         if (int rc = refiner_prologue_tile(p, a->radius, (unsigned char*)a->tile_done, st)) return rc;
         p.tile_done = (const unsigned char*)a->tile_done;
-        tile_count = tiles;
     }
     if (a->radius == 0 && 2 * a->cf + a->emb <= 32 && a->ldd <= 32 && p.vec_ok) {
         unsigned g = (unsigned)((pixels + 255) / 256);      // thin stride-1 maps: one thread per pixel
@@ -851,7 +833,6 @@ extern "C" int romab200_refiner_prologue(const rb_refiner_prologue_args* a, void
         return check_launch("refiner_prologue_small");
     }
     unsigned grid = (unsigned)((pixels + 3) / 4);
-    if (p.tile_done) grid = (unsigned)tile_count;                    // one CTA per tile of the cooperative pass
 #define LAUNCH(T, R) rb::launch_pdl(refiner_prologue_kernel<T, R>, dim3(grid), dim3(128), 0, st, p)
 #define BYR(T)                                                                                        \
     switch (a->radius) {                                                                              \

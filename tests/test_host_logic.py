@@ -229,3 +229,16 @@ def test_romatch_import_shim():
         sys.path.remove(shim)
         for m in [k for k in sys.modules if k == "romatch" or k.startswith("romatch.")]:
             del sys.modules[m]
+
+
+def test_prologue_tiles_matches_kernel_geometry():
+    """cabi.prologue_tiles (the size of the `tile_done` workspace callers allocate) follows the tile shapes compiled into the kernels."""
+    import os, re
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "roma_b200", "csrc", "refiner_common.cuh")).read()
+    generic = re.search(r"template <int R> struct LcTile \{ static constexpr int TQX = (\d+), TQY = (\d+)", text)
+    r7 = re.search(r"struct LcTile<7> \{ static constexpr int TQX = (\d+), TQY = (\d+)", text)
+    r2 = re.search(r"struct LcTile<2> \{ static constexpr int TQX = (\d+), TQY = (\d+)", text)
+    shapes = {3: tuple(map(int, generic.groups())), 7: tuple(map(int, r7.groups())), 2: tuple(map(int, r2.groups()))}
+    for r, (tx, ty) in shapes.items():
+        for h, w in ((40, 40), (70, 70), (108, 108), (13, 9), (1, 1)):
+            assert cabi.prologue_tiles(r, h, w) == -(-h // ty) * -(-w // tx), (r, h, w)
