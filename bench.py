@@ -519,7 +519,11 @@ def run_ours(args):
         return ew, ec
 
     parity = fast = None
-    if rank == 0:
+    if rank == 0 and args.model != "outdoor":
+        parity = {"ok": None, "tol": 1e-4,
+                  "note": "the 560->864 golden is the reference's output for the outdoor (seed-0) weights; roma_indoor (same graph, seed-1 weights) is pinned "
+                          "against the reference at 112->168 by tests/test_e2e_gpu.py::test_roma_indoor_vs_reference_golden"}
+    elif rank == 0:
         ew, ec = golden_errors(model)
         parity = {"warp": float(ew.max()), "certainty": float(ec.max()), "tol": 1e-4, "ok": bool(ew.max() <= 1e-4 and ec.max() <= 1e-4),
                   "reference": "tests/golden/full_sym_up.npz = output of the unmodified reference (CPU fp32) for the seed-1 560->864 pair, every 8th pixel",
