@@ -299,7 +299,10 @@ int romab200_match_epilogue(const rb_match_epilogue_args* args, void* stream);
 typedef struct { const float* x; float* density; int32_t n; float std; int32_t half;
                  /* optional: workspace of splits * n floats; the j range is then cut into `splits` parts summed in a fixed order by a second
                   * kernel (more CTAs than SMs for the 40000-point problem of sample()).  NULL / splits <= 1: one pass */
-                 float* workspace; int32_t splits; } rb_kde_args;
+                 float* workspace; int32_t splits;
+                 /* half mode only: evaluate the block pairs (I, J >= I) of 256 x 256 points once and credit both the row and the column sums
+                  * (exp(-d2) is symmetric); workspace of (splits + ceil(n / 256)) * n floats, its size in workspace_floats.  0: every pair twice */
+                 int32_t symmetric; int64_t workspace_floats; } rb_kde_args;
 int romab200_kde_density(const rb_kde_args* args, void* stream);
 
 /* sample(): weighted sampling WITHOUT replacement on the device (the two torch.multinomial draws of matcher.py:613-617, 626-628).

@@ -68,6 +68,7 @@ class Engine:
         self.fused_c144 = True                   # stride-2 refiner blocks as one fused DW + tcgen05-PW kernel
         self.lc_table16 = os.environ.get("ROMAB200_LC_TABLE16", "1") != "0"   # parity mode: stride-16 local correlation gathered from an all-pairs tensor-core table
         self.side_ctas = int(os.environ.get("ROMAB200_SIDE_CTAS", "0"))   # persistent-grid cap of the side stream's GEMMs (0: none)
+        self.kde_symmetric = os.environ.get("ROMAB200_KDE_SYM", "1") != "0"   # sample(): KDE over the upper triangle of the pair matrix
         self.lc_tile_radii = (2,)                # fp32 maps: window radii whose prologue also runs the tile-cooperative pass (measured: wins on coherent
                                                  # flow at r = 2, ties with the per-pixel kernel's L1 hits at r = 3; r = 7 uses the table above)
         self.fused_small_f32 = True              # fp32 modes: stride-1 (C = 24) refiner blocks as one fused fp32 CUDA-core kernel
@@ -670,6 +671,9 @@ class Engine:
         n = x.shape[0]
         out = torch.empty(n, dtype=torch.float32, device=x.device)
         splits = 16 if n >= 8192 else 1
-        ws = torch.empty(splits * n, dtype=torch.float32, device=x.device) if splits > 1 else None
-        call("romab200_kde_density", "rb_kde_args", x=x, density=out, n=n, std=std, half=int(half), workspace=ws, splits=splits)
+        sym = bool(half) and splits > 1 and self.kde_symmetric      # every pair once: (splits + blocks of 256) * n floats of workspace
+        nws = (splits + (n + 255) // 256) * n if sym else splits * n
+        ws = torch.empty(nws, dtype=torch.float32, device=x.device) if splits > 1 else None
+        call("romab200_kde_density", "rb_kde_args", x=x, density=out, n=n, std=std, half=int(half), workspace=ws, splits=splits,
+             symmetric=int(sym), workspace_floats=nws if ws is not None else 0)
         return out

@@ -7,9 +7,13 @@ dev = "cuda"
 n = 40000
 x = (torch.rand(n, 4, generator=torch.Generator().manual_seed(0)) * 2 - 1).to(dev)
 out = torch.empty(n, device=dev)
-for splits in (1, 2, 4, 8, 16):
-    ws = torch.empty(max(splits, 1) * n, device=dev)
-    fn = lambda: call("romab200_kde_density", "rb_kde_args", x=x, density=out, n=n, std=0.1, half=1, workspace=ws if splits > 1 else None, splits=splits)
+for splits in (1, 8, 16, -16):          # negative: the symmetric (upper-triangle) schedule with that many splits
+    sym = splits < 0
+    splits = abs(splits)
+    nws = (splits + (n + 255) // 256) * n if sym else max(splits, 1) * n
+    ws = torch.empty(nws, device=dev)
+    fn = lambda: call("romab200_kde_density", "rb_kde_args", x=x, density=out, n=n, std=0.1, half=1, workspace=ws if splits > 1 else None, splits=splits,
+                      symmetric=int(sym), workspace_floats=nws)
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         fn(); fn()
@@ -23,4 +27,4 @@ for splits in (1, 2, 4, 8, 16):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); g.replay(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) / 10)
-    print(f"splits {splits:2d}: {sorted(ts)[2]:.4f} ms, checksum {out.double().sum().item():.3f}")
+    print(f"splits {splits:2d}{" symmetric" if sym else ""}: {sorted(ts)[2]:.4f} ms, checksum {out.double().sum().item():.3f}")

@@ -517,6 +517,23 @@ def test_kde_density():
         outs32 = torch.zeros(n, device=DEV)
         call("romab200_kde_density", "rb_kde_args", x=x.to(DEV), density=outs32, n=n, std=0.1, half=0, workspace=ws, splits=splits)
         close(outs32, out32, 1e-4)
+    # symmetric schedule (every pair of 256-point blocks once, row and column sums credited): n = 3000 is 11.7 blocks (ragged last block)
+    for nn, splits in ((n, 1), (n, 3), (n, 64), (700, 2), (256, 4), (257, 2)):
+        xs = x[:nn].contiguous().to(DEV)
+        ref_n = torch.zeros(nn, device=DEV)
+        call("romab200_kde_density", "rb_kde_args", x=xs, density=ref_n, n=nn, std=0.1, half=1)
+        nws = (splits + (nn + 255) // 256) * nn
+        ws = torch.full((nws,), float("nan"), device=DEV)                   # every entry that is read must have been written
+        outs = torch.zeros(nn, device=DEV)
+        call("romab200_kde_density", "rb_kde_args", x=xs, density=outs, n=nn, std=0.1, half=1, workspace=ws, splits=splits, symmetric=1, workspace_floats=nws)
+        assert torch.isfinite(outs).all()
+        ulp = (ref_n.abs() * 2.0 ** -10).clamp_min(2.0 ** -14)
+        assert ((outs - ref_n).abs() <= 2 * ulp).all(), ((outs - ref_n).abs() / ulp).max().item()
+        assert ((outs - ref_n).abs() > 0).float().mean().item() < 0.05
+        refo = RomaOracle.kde(x[:nn]).float()
+        assert (((outs.cpu() - refo).abs() / refo.clamp_min(1.0)).max().item()) < 0.02
+    with pytest.raises(RuntimeError):
+        call("romab200_kde_density", "rb_kde_args", x=x.to(DEV), density=out, n=n, std=0.1, half=1, workspace=ws, splits=2, symmetric=1, workspace_floats=10)
 
 
 @pytest.mark.parametrize("mode", ["bilinear", "nearest"])
